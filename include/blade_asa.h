@@ -1,0 +1,160 @@
+/*
+ * blade_asa.h -- C ABI of the B200-native Adaptive Sparse Attention (ASA) hot path.
+ *
+ * Drop-in boundary for the kernels Video-BLADE's ASA module calls (reference paths relative to the
+ * VIDEO-BLADE tree; W = wanx/train/special_attentions_local/TrainRelated/wanx_blocksparseattn.py,
+ * C = cogvideox/.../cogvideo_blocksparseattn.py, P = .../attn_pooling_kernel.py):
+ *
+ *   reference interface                                              replaced by
+ *   ---------------------------------------------------------------  -----------------------------
+ *   GilbertRearranger.__init__ / gilbert3d        (W:102-129, G:6-167)  blade_gilbert_tables
+ *   index_select x3 + pad_to_multiple + simple_pooling
+ *                                     (W:25-36, 88-93, 142-152, 344-345)  blade_asa_prep
+ *   attn_with_pooling (Triton _attn_fwd)  (W:62-87 -> P:201-253)         blade_asa_scores_meanpool
+ *                                                                         blade_asa_scores_sampled
+ *   transfer_attn_to_mask(mode="energy")  (W:162-233, C:177-249)         blade_asa_select
+ *   block_sparse_attn -> block_sparse_attn_func (external CUDA lib)
+ *                                     (W:278-309, call site W:301-305)    blade_block_sparse_attn_fwd
+ *   standard_attn + LSE merge + reversed_rearrange
+ *                                     (W:21-24, 348-370, 154-159)         blade_asa_attn_fwd
+ *   AdaptiveBlockSparseAttnTrain.forward  (W:383-408, C:405-427)         blade_asa_forward
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer marked "device" is a CUDA device pointer owned by the
+ *     caller.  The library never allocates, frees or retains device memory: scratch comes from the
+ *     caller-provided workspace (size from blade_asa_workspace_bytes).
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - return 0 on success, a BLADE_ERR_* code otherwise; blade_last_error() gives the message of the
+ *     last failure on the calling thread.  No C++ exception crosses the boundary.
+ *   - tensors are [B, H, S, D] with ELEMENT strides (the reference passes transposed views of
+ *     [B, S, H, D] memory, modify_wan.py:104-106); the last dim must be contiguous.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BLADE_ASA_H_
+#define BLADE_ASA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLADE_ABI_VERSION 1
+
+enum BladeStatus {
+  BLADE_OK = 0,
+  BLADE_ERR_SHAPE = 1,      /* inconsistent / unsupported shape (W:250-251 asserts) */
+  BLADE_ERR_DTYPE = 2,      /* unsupported element type */
+  BLADE_ERR_ALIGN = 3,      /* pointer or stride not 16-byte aligned / last dim not contiguous */
+  BLADE_ERR_LAUNCH = 4,     /* CUDA launch / driver failure */
+  BLADE_ERR_ARG = 5,        /* bad argument (e.g. unknown mode, W:193-194,232 raise ValueError) */
+  BLADE_ERR_WORKSPACE = 6,  /* workspace too small */
+  BLADE_ERR_NO_DEVICE = 7   /* no sm_100 device */
+};
+
+enum BladeDType { BLADE_BF16 = 0, BLADE_F16 = 1, BLADE_F32 = 2, BLADE_I32 = 3, BLADE_U8 = 4 };
+
+typedef struct BladeTensor {
+  void* ptr;          /* device */
+  int64_t shape[4];   /* B, H, S, D */
+  int64_t stride[4];  /* element strides; stride[3] must be 1 */
+  int32_t dtype;      /* BladeDType */
+  int32_t _pad;
+} BladeTensor;
+
+/* Knobs of the reference module (W:9-16, C:9-16 and the literals W:62,325,341). */
+typedef struct BladeAsaConfig {
+  int32_t block_size;        /* 128 (W:325); 64 accepted for the selection/score stages */
+  int32_t sample_gap;        /* 30 wan / 15 cog (W:15); 0 disables the pooled branch */
+  int32_t min_retain;        /* max(1,int(nb*min_retain_ratio)) computed by the host (W:215 / C:230) */
+  int32_t max_retain;        /* max(1,int(nb*max_retain_ratio))                      (W:216 / C:231) */
+  float energy_threshold;    /* 0.95 (W:341) */
+  int32_t force_last;        /* 0 wan; 2 cog: last two block rows/cols forced on (C:247-248) */
+  int32_t num_keep;          /* 32 (W:62) -- sampled estimator only */
+  int32_t estimator;         /* 0 = block-mean-pool (north-star kernel (a)), 1 = sampled-max (P) */
+  int32_t exact_merge;       /* 1 = reproduce the reference's bf16 op chain W:351-370 (default) */
+  int32_t reserved[7];
+} BladeAsaConfig;
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int blade_abi_version(void);
+const char* blade_last_error(void);
+/* Returns BLADE_OK when a CUDA device with compute capability 10.x is current. */
+int blade_device_check(void);
+
+/* ---- a2: Gilbert curve tables (host memory, int64[w*h*d] each) ------------------------------ */
+int blade_gilbert_tables(int32_t width, int32_t height, int32_t depth,
+                         int64_t* curve2raster, int64_t* raster2curve);
+
+/* ---- workspace ------------------------------------------------------------------------------ */
+size_t blade_asa_workspace_bytes(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg);
+
+/* ---- prep: gather into curve order + block means + gap-pooled K/V ---------------------------
+ * src_row (device int32[S], may be NULL = identity): row of q/k/v that lands at output row r
+ *   (GilbertRearranger.rearrange, W:142-152 / C:141-154).
+ * q_r,k_r,v_r: contiguous [B,H,S,D] copies in output order (ptr may be NULL when src_row == NULL and
+ *   no copy is wanted).  q_mean,k_mean: fp32 [B,H,nb,D] means over replicate-padded blocks (W:25-36).
+ * k_pool,v_pool: [B,H,ceil(S/gap),D] in the input dtype, fp32-accumulated means (W:88-93). */
+int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                   const int32_t* src_row,
+                   void* q_r, void* k_r, void* v_r,
+                   float* q_mean, float* k_mean,
+                   void* k_pool, void* v_pool,
+                   int32_t block_size, int32_t sample_gap, void* stream);
+
+/* ---- score estimators: fp32 [B,H,nb,nb] row-normalised block scores -------------------------- */
+int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores,
+                              int64_t B, int64_t H, int64_t nb, int64_t D, void* stream);
+
+/* ---- a6: energy-threshold block selection ---------------------------------------------------
+ * scores fp32 [B,H,nq,nk] -> idx int32 [B,H,nq,nk] (ascending block ids, -1 padded),
+ * cnt int32 [B,H,nq], optional mask u8 [B,H,nq,nk], optional kcut int32 [B,H,nq].
+ * Order: value descending, block index ascending; prefix sums fp64-sequential rounded to fp32
+ * (== torch CPU sort(stable)+cumsum).  lo_bh/hi_bh: optional device int32[B*H] per-head bounds
+ * (C:230-231); NULL -> cfg->min_retain / max_retain. */
+int blade_asa_select(const float* scores, int64_t B, int64_t H, int64_t nq, int64_t nk,
+                     const BladeAsaConfig* cfg, const int32_t* lo_bh, const int32_t* hi_bh,
+                     int32_t* idx, int32_t* cnt, uint8_t* mask_opt, int32_t* kcut_opt, void* stream);
+
+/* bool block mask [B,H,nq,nk] (u8) -> idx/cnt in the same format (for callers that bring a mask). */
+int blade_mask_to_index(const uint8_t* mask, int64_t B, int64_t H, int64_t nq, int64_t nk,
+                        int32_t* idx, int32_t* cnt, void* stream);
+
+/* ---- a7/a8: block-sparse FlashAttention forward (replaces block_sparse_attn_func) -----------
+ * out [B,H,S,D] (any strides), lse fp32 [B,H,S] (natural log, may be NULL).
+ * dst_row: optional device int32[S]: output row r is written to row dst_row[r]. */
+int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                                BladeTensor* out, float* lse, const int32_t* dst_row,
+                                float softmax_scale, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a8+a10+a11: sparse branch + pooled branch + reference-exact LSE merge, one launch ------- */
+int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                       const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                       const BladeTensor* k_pool, const BladeTensor* v_pool, int32_t sample_gap,
+                       BladeTensor* out, const int32_t* dst_row,
+                       float softmax_scale, int32_t exact_merge,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a1: the whole layer (AdaptiveBlockSparseAttnTrain.forward) ------------------------------
+ * q,k,v in the caller's token order; src_row/dst_row as above (NULL = use_rearrange False).
+ * scores_in: optional fp32 [B,H,nb,nb] to bypass the estimator (parity contract);
+ * scores_out / mask_out / sparsity_sum (device float, += selected fraction numerator) optional. */
+int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                      const int32_t* src_row, const int32_t* dst_row,
+                      const BladeAsaConfig* cfg, const float* scores_in,
+                      BladeTensor* out, float* scores_out, uint8_t* mask_out,
+                      int32_t* idx_out, int32_t* cnt_out,
+                      void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- bring-up probes (tests only): single-tile tcgen05 GEMMs dumped from TMEM --------------- */
+int blade_probe_qk(const void* q_tile /*bf16 [128,D]*/, const void* k_tile /*bf16 [128,D]*/,
+                   float* s_out /*[128,128]*/, int32_t D, void* stream);
+int blade_probe_pv(const float* p_tile /*[128,128]*/, const void* v_tile /*bf16 [128,D]*/,
+                   float* o_out /*[128,D]*/, int32_t D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLADE_ASA_H_ */

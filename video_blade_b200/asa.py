@@ -1,0 +1,269 @@
+"""Host side of the ASA hot path: knobs, permutation tables, workspace and the C-ABI calls.
+
+Mirrors what the reference module does around its kernels
+(wanx_blocksparseattn.py W:311-408 / cogvideo_blocksparseattn.py C:327-427) but every tensor op of the
+reference (index_select, pad, topk, sort, cumsum, scatter, the two external attention calls, the merge)
+is one of the hand-written kernels behind include/blade_asa.h.  PyTorch is used for device memory and
+streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BladeAsaConfig, check, current_stream, ptr, tensor_desc
+
+
+@dataclass
+class AsaKnobs:
+    """The reference's module-level parameters (W:9-16 / C:9-16) plus its literals (W:62,325,341)."""
+    flavor: str = "wan"
+    use_rearrange: bool = True
+    max_retain_ratio: float = 0.17
+    min_retain_ratio: float = 0.05
+    width: int = 52
+    height: int = 30
+    depth: int = 21
+    sample_gap: int = 30
+    text_length: int = 0
+    block_size: int = 128
+    num_keep: int = 32
+    energy_threshold: float = 0.95
+    estimator: str = "meanpool"     # "meanpool" (north-star kernel (a)); "sampled_max" = reference P (next)
+    exact_merge: bool = True        # reproduce the bf16 op chain of W:351-370
+
+    @staticmethod
+    def wan(**kw) -> "AsaKnobs":
+        return AsaKnobs(flavor="wan", **kw)
+
+    @staticmethod
+    def cog(**kw) -> "AsaKnobs":
+        base = dict(flavor="cog", max_retain_ratio=0.1, width=45, height=30, depth=13, sample_gap=15,
+                    text_length=226)
+        base.update(kw)
+        return AsaKnobs(**base)
+
+    def retain_bounds(self, nb: int) -> Tuple[int, int]:
+        """W:215-216 (Python double arithmetic) / C:230-231 (fp32 tensor multiply, truncated)."""
+        if self.flavor == "cog":
+            lo = int(np.float32(nb) * np.float32(self.min_retain_ratio))
+            hi = int(np.float32(nb) * np.float32(self.max_retain_ratio))
+        else:
+            lo = int(nb * self.min_retain_ratio)
+            hi = int(nb * self.max_retain_ratio)
+        return max(1, lo), max(1, hi)
+
+    def c_config(self, nb: int) -> BladeAsaConfig:
+        lo, hi = self.retain_bounds(nb)
+        cfg = BladeAsaConfig()
+        cfg.block_size = self.block_size
+        cfg.sample_gap = self.sample_gap
+        cfg.min_retain = lo
+        cfg.max_retain = hi
+        cfg.energy_threshold = self.energy_threshold
+        cfg.force_last = 2 if self.flavor == "cog" else 0
+        cfg.num_keep = self.num_keep
+        cfg.estimator = 0 if self.estimator == "meanpool" else 1
+        cfg.exact_merge = 1 if self.exact_merge else 0
+        return cfg
+
+
+def gilbert_tables(width: int, height: int, depth: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(curve2raster, raster2curve) int64 arrays from the library's host implementation (W:102-129)."""
+    n = width * height * depth
+    c2r = np.empty(n, np.int64)
+    r2c = np.empty(n, np.int64)
+    check(_lib.load().blade_gilbert_tables(width, height, depth, c2r.ctypes.data, r2c.ctypes.data))
+    return c2r, r2c
+
+
+def token_order(knobs: AsaKnobs) -> np.ndarray:
+    """src_row[r] = index (in the caller's token order) of the token that sits at Gilbert-order row r.
+    wan: curve2raster (W:146-148).  cog: video tokens in curve order, then the text tokens that came first
+    (C:144-154).  The inverse move (W:154-159 / C:156-161) is a scatter through the same table."""
+    c2r, _ = gilbert_tables(knobs.width, knobs.height, knobs.depth)
+    if knobs.text_length:
+        t = knobs.text_length
+        return np.concatenate([c2r + t, np.arange(t, dtype=np.int64)]).astype(np.int32)
+    return c2r.astype(np.int32)
+
+
+class AsaEngine:
+    """Owns device-side tables + workspace for one (device, knobs) and drives the kernels."""
+
+    def __init__(self, knobs: AsaKnobs):
+        self.knobs = knobs
+        self.lib = _lib.load()
+        self._src_row = {}      # device -> int32 tensor
+        self._ws = {}           # (device, bytes) -> uint8 tensor
+        self._order_np: Optional[np.ndarray] = None
+
+    # ---- tables / workspace --------------------------------------------------------------
+    def src_row(self, device, S: int) -> Optional[torch.Tensor]:
+        if not self.knobs.use_rearrange:
+            return None
+        key = (str(device), S)
+        if key not in self._src_row:
+            if self._order_np is None:
+                self._order_np = token_order(self.knobs)
+            if self._order_np.size != S:
+                raise ValueError(
+                    f"sequence length {S} != width*height*depth + text_length = {self._order_np.size} "
+                    f"({self.knobs.width}x{self.knobs.height}x{self.knobs.depth}+{self.knobs.text_length})")
+            self._src_row[key] = torch.from_numpy(self._order_np).to(device)
+        return self._src_row[key]
+
+    def workspace(self, device, nbytes: int) -> torch.Tensor:
+        key = str(device)
+        cur = self._ws.get(key)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._ws[key] = cur
+        off = (-cur.data_ptr()) % 1024
+        return cur[off:off + nbytes]
+
+    @staticmethod
+    def _require_cuda(*ts):
+        for t in ts:
+            if t is not None and not t.is_cuda:
+                raise RuntimeError("video_blade_b200 runs on CUDA tensors only (no CPU fallback)")
+
+    # ---- stage entry points (same roles as the reference helpers) ------------------------
+    def select(self, scores: torch.Tensor, lo=None, hi=None, force_last=None, thr=None,
+               want_mask=True):
+        """transfer_attn_to_mask(mode='energy') on fp32 scores [B,H,nq,nk] -> (idx, cnt, mask)."""
+        self._require_cuda(scores)
+        assert scores.dtype == torch.float32
+        scores = scores.contiguous()
+        B, H, nq, nk = scores.shape
+        cfg = self.knobs.c_config(nk)
+        if lo is not None:
+            cfg.min_retain = int(lo)
+        if hi is not None:
+            cfg.max_retain = int(hi)
+        if force_last is not None:
+            cfg.force_last = int(force_last)
+        if thr is not None:
+            cfg.energy_threshold = float(thr)
+        idx = torch.empty(B, H, nq, nk, dtype=torch.int32, device=scores.device)
+        cnt = torch.empty(B, H, nq, dtype=torch.int32, device=scores.device)
+        mask = torch.empty(B, H, nq, nk, dtype=torch.uint8, device=scores.device) if want_mask else None
+        check(self.lib.blade_asa_select(scores.data_ptr(), B, H, nq, nk, C.byref(cfg), None, None,
+                                        idx.data_ptr(), cnt.data_ptr(), ptr(mask), None, current_stream()))
+        return idx, cnt, (mask.bool() if want_mask else None)
+
+    def mask_to_index(self, mask: torch.Tensor):
+        self._require_cuda(mask)
+        m = mask.to(torch.uint8).contiguous()
+        B, H, nq, nk = m.shape
+        idx = torch.empty(B, H, nq, nk, dtype=torch.int32, device=m.device)
+        cnt = torch.empty(B, H, nq, dtype=torch.int32, device=m.device)
+        check(self.lib.blade_mask_to_index(m.data_ptr(), B, H, nq, nk, idx.data_ptr(), cnt.data_ptr(),
+                                           current_stream()))
+        return idx, cnt
+
+    def prep(self, q, k, v, rearrange: bool, want_means=True, want_pool=True):
+        """Gather into Gilbert order (optional) + block means + gap-pooled K/V."""
+        self._require_cuda(q, k, v)
+        B, H, S, D = q.shape
+        kn = self.knobs
+        dev = q.device
+        src = self.src_row(dev, S) if rearrange else None
+        nb = -(-S // kn.block_size)
+        q_r = k_r = v_r = None
+        if src is not None:
+            q_r = torch.empty(B, H, S, D, dtype=q.dtype, device=dev)
+            k_r = torch.empty_like(q_r)
+            v_r = torch.empty_like(q_r)
+        qm = km = kp = vp = None
+        if want_means:
+            qm = torch.empty(B, H, nb, D, dtype=torch.float32, device=dev)
+            km = torch.empty_like(qm)
+        gap = kn.sample_gap if want_pool else 0
+        if gap:
+            npool = -(-S // gap)
+            kp = torch.empty(B, H, npool, D, dtype=q.dtype, device=dev)
+            vp = torch.empty_like(kp)
+        check(self.lib.blade_asa_prep(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)),
+                                      ptr(src), ptr(q_r), ptr(k_r), ptr(v_r), ptr(qm), ptr(km), ptr(kp), ptr(vp),
+                                      kn.block_size, gap, current_stream()))
+        return (q_r, k_r, v_r), (qm, km), (kp, vp)
+
+    def scores_meanpool(self, qm: torch.Tensor, km: torch.Tensor) -> torch.Tensor:
+        B, H, nb, D = qm.shape
+        sc = torch.empty(B, H, nb, nb, dtype=torch.float32, device=qm.device)
+        check(self.lib.blade_asa_scores_meanpool(qm.data_ptr(), km.data_ptr(), sc.data_ptr(), B, H, nb, D,
+                                                 current_stream()))
+        return sc
+
+    def _park(self, device, D):
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        return self.workspace(device, sms * 2 * (D // 8) * 128 * 16)
+
+    def block_sparse_attn(self, q, k, v, idx, cnt, out=None, dst_row=None, want_lse=True):
+        """block_sparse_attn(q,k,v,block_mask) (W:278-309) on an index list; returns (out, lse fp32 [B,H,S])."""
+        self._require_cuda(q, k, v, idx, cnt)
+        B, H, S, D = q.shape
+        if out is None:
+            out = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
+        lse = torch.empty(B, H, S, dtype=torch.float32, device=q.device) if want_lse else None
+        ws = self._park(q.device, D)
+        od = tensor_desc(out)
+        check(self.lib.blade_block_sparse_attn_fwd(
+            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), idx.data_ptr(), cnt.data_ptr(),
+            idx.shape[-1], C.byref(od), ptr(lse), ptr(dst_row), 1.0 / math.sqrt(D), ws.data_ptr(), ws.numel(),
+            current_stream()))
+        return out, lse
+
+    def asa_attn(self, q, k, v, idx, cnt, k_pool, v_pool, out=None, dst_row=None, exact_merge=None):
+        """Sparse branch + pooled branch + merge (W:343-370) in one launch."""
+        self._require_cuda(q, k, v, idx, cnt, k_pool, v_pool)
+        B, H, S, D = q.shape
+        if out is None:
+            out = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
+        ws = self._park(q.device, D)
+        em = self.knobs.exact_merge if exact_merge is None else exact_merge
+        check(self.lib.blade_asa_attn_fwd(
+            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), idx.data_ptr(), cnt.data_ptr(),
+            idx.shape[-1], C.byref(tensor_desc(k_pool)), C.byref(tensor_desc(v_pool)), self.knobs.sample_gap,
+            C.byref(tensor_desc(out)), ptr(dst_row), 1.0 / math.sqrt(D), 1 if em else 0, ws.data_ptr(), ws.numel(),
+            current_stream()))
+        return out
+
+    # ---- the whole layer ------------------------------------------------------------------
+    def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False):
+        """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
+        token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
+        processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous."""
+        self._require_cuda(q, k, v, scores)
+        B, H, S, D = q.shape
+        kn = self.knobs
+        dev = q.device
+        nb = -(-S // kn.block_size)
+        cfg = kn.c_config(nb)
+        src = self.src_row(dev, S)
+        nbytes = self.lib.blade_asa_workspace_bytes(B, H, S, D, C.byref(cfg))
+        ws = self.workspace(dev, nbytes)
+        out = torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)
+        cnt = torch.empty(B, H, nb, dtype=torch.int32, device=dev)
+        sc_out = mask = idx = None
+        if return_debug:
+            sc_out = torch.empty(B, H, nb, nb, dtype=torch.float32, device=dev)
+            mask = torch.empty(B, H, nb, nb, dtype=torch.uint8, device=dev)
+            idx = torch.empty(B, H, nb, nb, dtype=torch.int32, device=dev)
+        if scores is not None:
+            scores = scores.contiguous()
+            assert scores.dtype == torch.float32 and tuple(scores.shape) == (B, H, nb, nb)
+        check(self.lib.blade_asa_forward(
+            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), ptr(src), ptr(src),
+            C.byref(cfg), ptr(scores), C.byref(tensor_desc(out)), ptr(sc_out), ptr(mask), ptr(idx), cnt.data_ptr(),
+            ws.data_ptr(), ws.numel(), current_stream()))
+        if return_debug:
+            return out, dict(scores=sc_out, mask=mask.bool(), idx=idx, cnt=cnt)
+        return out, cnt

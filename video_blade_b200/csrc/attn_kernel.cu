@@ -1,0 +1,753 @@
+// attn_kernel.cu -- north-star kernel (b): block-sparse FlashAttention forward for sm_100a.
+//
+// Replaces the reference's two calls into the external mit-han-lab `block_sparse_attn_func`
+// (sparse branch W:301-305 via W:278-309, pooled "global" branch W:21-24,348) and the LSE merge
+// (W:351-370) with ONE persistent, warp-specialised kernel:
+//
+//   * work item  = one head x one PAIR of adjacent 128-row query tiles; the two tiles are two independent
+//     "streams" that ping-pong on the tensor core (while one stream is in softmax the other is in MMA);
+//   * per stream the KV sequence is [pooled tiles ..., selected blocks ...]: the pooled branch and the
+//     sparse branch run back to back through the same pipeline with separate (m, l, O) state, because the
+//     reference merges them with a chain of bf16 element-wise ops that a single fused softmax does not
+//     reproduce; the pooled result is parked (bf16) in a small L2-resident workspace;
+//   * warp 8 lane 0: TMA producer (Q tiles + a 5-deep ring of 128x128 K / V tiles, SWIZZLE_128B);
+//     warp 9 lane 0: tcgen05.mma issuer -- S = Q K^T (SS, both operands K-major in smem, fp32 in TMEM),
+//                    O += P V (TS: P read from TMEM where the softmax wrote it as bf16 over S, V MN-major);
+//     warps 0-3 / 4-7: softmax warpgroups of stream 0 / 1: one query row per thread, tcgen05.ld of the
+//                    128-column S row, online softmax in registers with lazy O rescale (threshold 2^8),
+//                    tcgen05.st of P, final normalise + merge + (inverse-Gilbert) row store;
+//   * TMEM map (512 columns): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [256+D,256+2D).
+//
+// All synchronisation is mbarrier based (TMA complete_tx, tcgen05.commit, thread arrivals).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace blade {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 128;
+constexpr int kThreads = 384;
+constexpr int kSoftmaxThreads = 128;
+constexpr float kRescaleThresh = 8.0f;  // log2 units
+constexpr int kMaxListSmem = 256;       // per-stream block ids cached in smem by the producer
+constexpr float kLn2 = 0.69314718055994530942f;
+
+template <int D>
+struct SmemLayout {
+  static constexpr int kTileBytes = kBlockN * D * 2;  // one K or V tile == one Q tile
+  static constexpr int kStages = D == 128 ? 5 : 10;
+  static constexpr int kQOff = 0;
+  static constexpr int kKVOff = 2 * kTileBytes;
+  static constexpr int kMiscOff = kKVOff + kStages * kTileBytes;
+  static constexpr int kMiscBytes = 2048;
+  static constexpr int kTotal = kMiscOff + kMiscBytes + 1024;  // + worst-case alignment slack
+};
+
+struct Misc {
+  uint64_t q_full[2], q_empty[2];
+  uint64_t s_full[2], p_full[2], o_full[2];
+  uint64_t kv_full[10], kv_empty[10];
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint16_t list[2][kMaxListSmem];
+};
+static_assert(sizeof(Misc) <= 2048, "misc smem region overflow");
+
+struct AttnParams {
+  const int32_t* idx;
+  const int32_t* cnt;
+  int64_t idx_stride;
+  uint16_t* out;
+  int64_t out_sb, out_sh, out_ss;
+  float* lse;              // optional fp32 [B,H,S] (sparse-branch lse), may be null
+  const int32_t* dst_row;  // optional
+  uint4* park;             // [grid][2][D/8][128] 16-byte chunks (pooled-branch output)
+  int B, H, S, nq, nk;
+  int n_pool, n_pool_tiles;
+  int num_items, pairs_per_head;
+  float scale_log2;        // softmax_scale * log2(e)
+  float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
+  float gap;               // float(sample_gap) for the non-emulated merge
+  int exact_merge;
+};
+
+template <bool IS_BF16>
+__device__ __forceinline__ float round_t(float x) {
+  return IS_BF16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
+}
+template <bool IS_BF16>
+__device__ __forceinline__ uint32_t pack_t(float lo, float hi) {
+  return IS_BF16 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi);
+}
+template <bool IS_BF16>
+__device__ __forceinline__ float2 unpack_t(uint32_t w) {
+  if (IS_BF16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+
+// K-major SWIZZLE_128B operand tile [128 rows][D] stored as D/64 sub-tiles of [128][64] (16 KB each):
+// descriptor start offset (in 16-byte units) of the k-th 16-element K slice.
+template <int D>
+__device__ __forceinline__ uint32_t kmajor_koff(int k) {
+  return static_cast<uint32_t>((k >> 2) * (kBlockN * 128 / 16) + (k & 3) * 2);
+}
+
+// ================================================================================================
+template <int D, bool IS_BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
+                const __grid_constant__ CUtensorMap tmVp, const AttnParams p) {
+  using L = SmemLayout<D>;
+  constexpr int kStages = L::kStages;
+  constexpr int kTileBytes = L::kTileBytes;
+  constexpr int kSub = D / 64;  // 64-column sub-tiles per operand tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + L::kQOff;
+  uint8_t* sKV = smem + L::kKVOff;
+  Misc* mz = reinterpret_cast<Misc*>(smem + L::kMiscOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&mz->q_full[t], 1);
+      mbar_init(&mz->q_empty[t], 1);
+      mbar_init(&mz->s_full[t], 1);
+      mbar_init(&mz->p_full[t], kSoftmaxThreads);
+      mbar_init(&mz->o_full[t], 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&mz->kv_full[s], 1);
+      mbar_init(&mz->kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 11) tmem_alloc<512>(&mz->tmem_base);
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    if (p.n_pool_tiles) {
+      tma_prefetch_desc(&tmKp);
+      tma_prefetch_desc(&tmVp);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = mz->tmem_base;
+
+  const int npt = p.n_pool_tiles;
+
+  if (warp == 8) {
+    // ============================== TMA producer ==============================
+    uint32_t kv_n = 0;
+    uint32_t q_it[2] = {0, 0};
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+      const int b = bh / p.H, h = bh % p.H;
+      int ns[2], nt[2];
+      const int32_t* lists[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int qb = 2 * pair + t;
+        const bool valid = qb < p.nq;
+        const int64_t row = static_cast<int64_t>(bh) * p.nq + qb;
+        ns[t] = valid ? __ldg(p.cnt + row) : 0;
+        nt[t] = valid ? npt + ns[t] : 0;
+        lists[t] = p.idx + row * p.idx_stride;
+        // cooperative, coalesced fetch of the block-id list into smem
+        for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32) mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j));
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (nt[t] == 0) continue;
+          mbar_wait(&mz->q_empty[t], (q_it[t] & 1) ^ 1);
+          mbar_arrive_expect_tx(&mz->q_full[t], kTileBytes);
+#pragma unroll
+          for (int dh = 0; dh < kSub; ++dh)
+            tma_load_4d(sQ + t * kTileBytes + dh * (kBlockM * 128), &tmQ, &mz->q_full[t], dh * 64,
+                        (2 * pair + t) * kBlockM, h, b, kEvictFirst);
+          ++q_it[t];
+        }
+        auto load_tile = [&](int t, int j, bool is_v) {
+          const uint32_t slot = kv_n % kStages;
+          mbar_wait(&mz->kv_empty[slot], ((kv_n / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&mz->kv_full[slot], kTileBytes);
+          const CUtensorMap* map;
+          int row;
+          if (j < npt) {
+            map = is_v ? &tmVp : &tmKp;
+            row = j * kBlockN;
+          } else {
+            const int jj = j - npt;
+            const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : __ldg(lists[t] + jj);
+            map = is_v ? &tmV : &tmK;
+            row = kb * kBlockN;
+          }
+#pragma unroll
+          for (int dh = 0; dh < kSub; ++dh)
+            tma_load_4d(sKV + slot * kTileBytes + dh * (kBlockN * 128), map, &mz->kv_full[slot], dh * 64, row, h, b,
+                        kEvictLast);
+          ++kv_n;
+        };
+        const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
+        if (nt[0]) load_tile(0, 0, false);
+        if (nt[1]) load_tile(1, 0, false);
+        for (int j = 0; j < nmax; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j < nt[t]) {
+              load_tile(t, j, true);
+              if (j + 1 < nt[t]) load_tile(t, j + 1, false);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kBlockM, kBlockN, IS_BF16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kBlockM, D, IS_BF16, false, true);
+      uint32_t kv_c = 0;
+      uint32_t g[2] = {0, 0};
+      uint32_t q_it[2] = {0, 0};
+      const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+        int nt[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int qb = 2 * pair + t;
+          nt[t] = qb < p.nq ? npt + __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb) : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (nt[t] == 0) continue;
+          mbar_wait(&mz->q_full[t], q_it[t] & 1);
+          ++q_it[t];
+        }
+        tc_fence_after();
+        auto issue_qk = [&](int t, bool last) {
+          const uint32_t slot = kv_c % kStages;
+          mbar_wait(&mz->kv_full[slot], (kv_c / kStages) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sQ_addr + t * kTileBytes, 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, 16, 1024, 2);
+          const uint32_t tS = tmem_base + t * kBlockN;
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            umma_ss(tS, adesc + kmajor_koff<D>(k), bdesc + kmajor_koff<D>(k), idesc_qk, k > 0);
+          tc_commit(&mz->kv_empty[slot]);
+          tc_commit(&mz->s_full[t]);
+          if (last) tc_commit(&mz->q_empty[t]);
+          ++kv_c;
+        };
+        auto issue_pv = [&](int t, bool fresh) {
+          mbar_wait(&mz->p_full[t], g[t] & 1);
+          const uint32_t slot = kv_c % kStages;
+          mbar_wait(&mz->kv_full[slot], (kv_c / kStages) & 1);
+          tc_fence_after();
+          // V tile: [kv 128][D] as D/64 sub-tiles [128][64], MN-major for B: LBO = sub-tile stride, SBO = 8 kv rows
+          const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, kBlockN * 128, 1024, 2);
+          const uint32_t tP = tmem_base + t * kBlockN;
+          const uint32_t tO = tmem_base + 2 * kBlockN + t * D;
+#pragma unroll
+          for (int k = 0; k < kBlockN / 16; ++k)
+            umma_ts(tO, tP + k * 8, bdesc + k * (16 * 128 / 16), idesc_pv, (!fresh) || k > 0);
+          tc_commit(&mz->kv_empty[slot]);
+          tc_commit(&mz->o_full[t]);
+          ++kv_c;
+          ++g[t];
+        };
+        const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
+        if (nt[0]) issue_qk(0, nt[0] == 1);
+        if (nt[1]) issue_qk(1, nt[1] == 1);
+        for (int j = 0; j < nmax; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j < nt[t]) {
+              issue_pv(t, j == 0 || j == npt);
+              if (j + 1 < nt[t]) issue_qk(t, j + 2 == nt[t]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // ============================== softmax warpgroups ==============================
+    const int t = warp >> 2;
+    const int wq = warp & 3;
+    const int row_in_tile = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * kBlockN;
+    const uint32_t tO = tmem_base + lane_base + 2 * kBlockN + t * D;
+    uint4* park = p.park + (static_cast<size_t>(blockIdx.x) * 2 + t) * (D / 8) * kBlockM;
+    uint32_t g = 0;
+    const float sl2 = p.scale_log2;
+    const int pool_tail = p.n_pool - (npt - 1) * kBlockN;
+    const int seq_tail = p.S - (p.nk - 1) * kBlockN;  // valid keys in the last key block
+
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+      const int b = bh / p.H, h = bh % p.H;
+      const int qb = 2 * pair + t;
+      if (qb >= p.nq) continue;
+      const int64_t lrow = static_cast<int64_t>(bh) * p.nq + qb;
+      const int ns = __ldg(p.cnt + lrow);
+      const int last_kb = ns > 0 ? __ldg(p.idx + lrow * p.idx_stride + ns - 1) : -1;
+      const int sparse_tail = (last_kb == p.nk - 1) ? seq_tail : kBlockN;
+      float lse2 = 0.f;
+
+      for (int phase = (npt ? 0 : 1); phase < 2; ++phase) {
+        const int ntile = phase == 0 ? npt : ns;
+        const int tail_valid = phase == 0 ? pool_tail : sparse_tail;
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < ntile; ++j, ++g) {
+          mbar_wait(&mz->s_full[t], g & 1);
+          tc_fence_after();
+          uint32_t s[4][32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+          tmem_wait_ld();
+          const int valid = (j == ntile - 1) ? tail_valid : kBlockN;
+          float mx = -INFINITY;
+          if (valid < kBlockN) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+                mx = fmaxf(mx, __uint_as_float(s[c][i]));
+              }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+          }
+          mx *= sl2;
+          if (j == 0) {
+            m = mx;
+          } else {
+            const float m_cand = fmaxf(m, mx);
+            const bool need = (m_cand - m) > kRescaleThresh;
+            if (__any_sync(0xffffffffu, need)) {
+              const float m_new = need ? m_cand : m;
+              const float alpha = ex2_approx(m - m_new);
+              mbar_wait(&mz->o_full[t], (g - 1) & 1);  // PV of the previous tile has retired
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < D / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tO + c * 32, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tO + c * 32, o);
+              }
+              tmem_wait_st();
+              l *= alpha;
+              m = m_new;
+            }
+          }
+          const float neg_m = -m;
+          float lsum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), sl2, neg_m));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, neg_m));
+              lsum += p0 + p1;
+              pk[i] = pack_t<IS_BF16>(p0, p1);
+            }
+            tmem_st16(tS + c * 16, pk);
+          }
+          l += lsum;
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&mz->p_full[t]);
+        }
+        // ---- phase finalisation: the last PV of this phase has to retire first
+        mbar_wait(&mz->o_full[t], (g - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const float lse = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
+        if (phase == 0) {
+          lse2 = lse;
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 w;
+              w.x = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 0]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l);
+              w.y = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
+              w.z = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
+              w.w = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
+              park[(c * 4 + u) * kBlockM + row_in_tile] = w;
+            }
+          }
+        } else {
+          const int r = qb * kBlockM + row_in_tile;
+          const bool store = r < p.S;
+          float alpha = 1.f, oma = 0.f;
+          if (npt) {
+            if (p.exact_merge) {
+              // W:351-370 op by op, every intermediate rounded to the tensor dtype (lse already is, W:309)
+              const float a = round_t<IS_BF16>(lse);
+              const float b2 = round_t<IS_BF16>(round_t<IS_BF16>(lse2) + p.log_gap_r);
+              const float mxw = fmaxf(a, b2);
+              const float e1 = round_t<IS_BF16>(expf(round_t<IS_BF16>(a - mxw)));
+              const float e2 = round_t<IS_BF16>(expf(round_t<IS_BF16>(b2 - mxw)));
+              alpha = round_t<IS_BF16>(e1 / round_t<IS_BF16>(e1 + e2));
+              oma = round_t<IS_BF16>(1.0f - alpha);
+            } else {
+              alpha = 1.0f / (1.0f + p.gap * expf(lse2 - lse));
+              oma = 1.0f - alpha;
+            }
+          }
+          int dst = r;
+          if (store && p.dst_row) dst = __ldg(p.dst_row + r);
+          uint16_t* orow = p.out + b * p.out_sb + h * p.out_sh + static_cast<int64_t>(dst) * p.out_ss;
+          if (store && p.lse) p.lse[static_cast<int64_t>(bh) * p.S + r] = lse;
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * u + i]) * inv_l;
+              if (npt) {
+                const uint4 w2 = park[(c * 4 + u) * kBlockM + row_in_tile];
+                const uint32_t ww[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 o2 = unpack_t<IS_BF16>(ww[i]);
+                  if (p.exact_merge) {
+                    const float x0 = round_t<IS_BF16>(round_t<IS_BF16>(f[2 * i]) * alpha);
+                    const float x1 = round_t<IS_BF16>(round_t<IS_BF16>(f[2 * i + 1]) * alpha);
+                    const float y0 = round_t<IS_BF16>(o2.x * oma);
+                    const float y1 = round_t<IS_BF16>(o2.y * oma);
+                    f[2 * i] = x0 + y0;
+                    f[2 * i + 1] = x1 + y1;
+                  } else {
+                    f[2 * i] = f[2 * i] * alpha + o2.x * oma;
+                    f[2 * i + 1] = f[2 * i + 1] * alpha + o2.y * oma;
+                  }
+                }
+              }
+              uint4 w;
+              w.x = pack_t<IS_BF16>(f[0], f[1]);
+              w.y = pack_t<IS_BF16>(f[2], f[3]);
+              w.z = pack_t<IS_BF16>(f[4], f[5]);
+              w.w = pack_t<IS_BF16>(f[6], f[7]);
+              if (store) reinterpret_cast<uint4*>(orow)[c * 4 + u] = w;
+            }
+          }
+        }
+        // O_t / S_t are handed back implicitly: the next PV of this stream waits for our next p_full.
+        tc_fence_before();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) tmem_dealloc<512>(tmem_base);
+}
+
+// ================================================================================================
+// bring-up probes: one tile through the same descriptors / TMEM layouts as the main kernel
+// ================================================================================================
+template <int D>
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* p_in,
+             float* out, int mode /*0 = QK^T, 1 = PV*/) {
+  constexpr int kTileBytes = kBlockN * D * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTileBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+
+  if (mode == 1) {
+    // P (fp32 [128][128]) -> bf16 pairs in TMEM columns [0,64)
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+      for (int i = 0; i < 16; ++i)
+        pk[i] = pack_bf16x2(p_in[row * kBlockN + c * 32 + 2 * i], p_in[row * kBlockN + c * 32 + 2 * i + 1]);
+      tmem_st16(tmem_base + lane_base + c * 16, pk);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    mbar_arrive_expect_tx(&bars[0], mode == 0 ? 2 * kTileBytes : kTileBytes);
+    for (int dh = 0; dh < D / 64; ++dh) {
+      if (mode == 0) tma_load_4d(sA + dh * (kBlockM * 128), &tmA, &bars[0], dh * 64, 0, 0, 0, kEvictNormal);
+      tma_load_4d(sB + dh * (kBlockN * 128), &tmB, &bars[0], dh * 64, 0, 0, 0, kEvictNormal);
+    }
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    if (mode == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, kBlockN, true, false, false);
+      const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, 2);
+      const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, 2);
+      for (int k = 0; k < D / 16; ++k)
+        umma_ss(tmem_base + 128, adesc + kmajor_koff<D>(k), bdesc + kmajor_koff<D>(k), idesc, k > 0);
+    } else {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, D, true, false, true);
+      const uint64_t bdesc = make_smem_desc(smem_u32(sB), kBlockN * 128, 1024, 2);
+      for (int k = 0; k < kBlockN / 16; ++k)
+        umma_ts(tmem_base + 128, tmem_base + k * 8, bdesc + k * (16 * 128 / 16), idesc, k > 0);
+    }
+    tc_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int ncols = mode == 0 ? kBlockN : D;
+  for (int c = 0; c < ncols / 32; ++c) {
+    uint32_t o[32];
+    tmem_ld32(tmem_base + lane_base + 128 + c * 32, o);
+    tmem_wait_ld();
+    for (int i = 0; i < 32; ++i) out[row * ncols + c * 32 + i] = __uint_as_float(o[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ================================================================================================
+// host side: tensor maps + launch
+// ================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// [B,H,S,D] 16-bit tensor with element strides -> 4-D map, box = 64 x 128 x 1 x 1, SWIZZLE_128B
+static int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int64_t B, int64_t H, int64_t S, int64_t D,
+                     int64_t sb, int64_t sh, int64_t ss) {
+  PFN_encodeTiled enc = get_encode();
+  BLADE_REQUIRE(enc != nullptr, BLADE_ERR_LAUNCH, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)(ss * 2), (cuuint64_t)(sh * 2), (cuuint64_t)(sb * 2)};
+  // size-1 dims may carry arbitrary strides; TMA wants multiples of 16 bytes
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0 || strides[i] == 0) strides[i] = (cuuint64_t)(D * 2);
+  cuuint32_t box[4] = {64, (cuuint32_t)kBlockN, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dtype == BLADE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BLADE_REQUIRE(r == CUDA_SUCCESS, BLADE_ERR_LAUNCH, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return BLADE_OK;
+}
+static int make_tmap(CUtensorMap* map, const BladeTensor* t) {
+  return make_tmap(map, t->ptr, t->dtype, t->shape[0], t->shape[1], t->shape[2], t->shape[3], t->stride[0],
+                   t->stride[1], t->stride[2]);
+}
+
+static int device_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+size_t attn_park_bytes(int64_t D) { return static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16; }
+
+static float round_host(float x, bool bf16) {
+  return bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
+}
+
+int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
+                const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
+                int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (int e = check_tensor16(q, "q")) return e;
+  if (int e = check_tensor16(k, "k")) return e;
+  if (int e = check_tensor16(v, "v")) return e;
+  if (int e = check_tensor16(out, "out")) return e;
+  BLADE_REQUIRE(idx && cnt, BLADE_ERR_ARG, "idx/cnt null");
+  const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
+  const int64_t Sk = k->shape[2];
+  for (int i = 0; i < 4; ++i) {
+    BLADE_REQUIRE(v->shape[i] == k->shape[i], BLADE_ERR_SHAPE, "k/v shapes differ in dim %d", i);
+    BLADE_REQUIRE(out->shape[i] == q->shape[i], BLADE_ERR_SHAPE, "out/q shapes differ in dim %d", i);
+    if (i != 2) BLADE_REQUIRE(k->shape[i] == q->shape[i], BLADE_ERR_SHAPE, "q/k shapes differ in dim %d", i);
+  }
+  BLADE_REQUIRE(q->dtype == k->dtype && q->dtype == v->dtype && q->dtype == out->dtype, BLADE_ERR_DTYPE,
+                "q/k/v/out dtypes differ");
+  BLADE_REQUIRE(S < (1 << 30) && Sk < (1 << 30), BLADE_ERR_SHAPE, "sequence too long");
+  const int nq = (int)ceil_div(S, kBlockM), nk = (int)ceil_div(Sk, kBlockN);
+  BLADE_REQUIRE(nk <= 65535, BLADE_ERR_SHAPE, "too many key blocks");
+  BLADE_REQUIRE(idx_stride >= 1, BLADE_ERR_ARG, "idx_stride");
+  const bool pooled = sample_gap > 0 && k_pool && v_pool && k_pool->ptr && v_pool->ptr;
+  int n_pool = 0;
+  if (pooled) {
+    if (int e = check_tensor16(k_pool, "k_pool")) return e;
+    if (int e = check_tensor16(v_pool, "v_pool")) return e;
+    n_pool = (int)k_pool->shape[2];
+    BLADE_REQUIRE(v_pool->shape[2] == n_pool && k_pool->shape[3] == D && k_pool->shape[0] == B &&
+                      k_pool->shape[1] == H && n_pool >= 1,
+                  BLADE_ERR_SHAPE, "pooled k/v shape mismatch");
+    BLADE_REQUIRE(workspace && ws_bytes >= attn_park_bytes(D), BLADE_ERR_WORKSPACE,
+                  "attention workspace too small: need %zu bytes", attn_park_bytes(D));
+    BLADE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, BLADE_ERR_ALIGN, "workspace not 16B aligned");
+  }
+  const bool bf = q->dtype == BLADE_BF16;
+
+  CUtensorMap tmQ, tmK, tmV, tmKp, tmVp;
+  if (int e = make_tmap(&tmQ, q)) return e;
+  if (int e = make_tmap(&tmK, k)) return e;
+  if (int e = make_tmap(&tmV, v)) return e;
+  if (pooled) {
+    if (int e = make_tmap(&tmKp, k_pool)) return e;
+    if (int e = make_tmap(&tmVp, v_pool)) return e;
+  } else {
+    tmKp = tmK;
+    tmVp = tmV;
+  }
+
+  AttnParams p{};
+  p.idx = idx;
+  p.cnt = cnt;
+  p.idx_stride = idx_stride;
+  p.out = static_cast<uint16_t*>(out->ptr);
+  p.out_sb = out->stride[0];
+  p.out_sh = out->stride[1];
+  p.out_ss = out->stride[2];
+  p.lse = lse;
+  p.dst_row = dst_row;
+  p.park = static_cast<uint4*>(workspace);
+  p.B = (int)B;
+  p.H = (int)H;
+  p.S = (int)S;
+  p.nq = nq;
+  p.nk = nk;
+  p.n_pool = n_pool;
+  p.n_pool_tiles = pooled ? (int)ceil_div(n_pool, kBlockN) : 0;
+  p.pairs_per_head = (nq + 1) / 2;
+  p.num_items = (int)(B * H) * p.pairs_per_head;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.gap = (float)sample_gap;
+  p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;
+  p.exact_merge = exact_merge;
+
+  const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
+#define LAUNCH_ATTN(DD, BF)                                                                                     \
+  do {                                                                                                          \
+    auto kern = asa_attn_kernel<DD, BF>;                                                                        \
+    BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<DD>::kTotal)); \
+    kern<<<grid, kThreads, SmemLayout<DD>::kTotal, stream>>>(tmQ, tmK, tmV, tmKp, tmVp, p);                      \
+  } while (0)
+  if (D == 128) { if (bf) LAUNCH_ATTN(128, true); else LAUNCH_ATTN(128, false); }
+  else          { if (bf) LAUNCH_ATTN(64, true); else LAUNCH_ATTN(64, false); }
+#undef LAUNCH_ATTN
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+int launch_probe(const void* a_tile, const void* b_tile, const float* p_in, float* out, int D, int mode,
+                 cudaStream_t stream) {
+  BLADE_REQUIRE(D == 64 || D == 128, BLADE_ERR_SHAPE, "probe D");
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap(&tmA, mode == 0 ? a_tile : b_tile, BLADE_BF16, 1, 1, 128, D, 128 * D, 128 * D, D)) return e;
+  if (int e = make_tmap(&tmB, b_tile, BLADE_BF16, 1, 1, 128, D, 128 * D, 128 * D, D)) return e;
+  const int smem = 2 * kBlockN * D * 2 + 1024 + 256;
+  if (D == 128) {
+    BLADE_CUDA_OK(cudaFuncSetAttribute(probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_kernel<128><<<1, 128, smem, stream>>>(tmA, tmB, p_in, out, mode);
+  } else {
+    BLADE_CUDA_OK(cudaFuncSetAttribute(probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_kernel<64><<<1, 128, smem, stream>>>(tmA, tmB, p_in, out, mode);
+  }
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+}  // namespace blade
+
+using namespace blade;
+
+extern "C" int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                           const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                                           BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
+                                           void* workspace, size_t ws_bytes, void* stream) {
+  return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
+                     ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
+                                  const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool,
+                                  const BladeTensor* v_pool, int32_t sample_gap, BladeTensor* out,
+                                  const int32_t* dst_row, float softmax_scale, int32_t exact_merge, void* workspace,
+                                  size_t ws_bytes, void* stream) {
+  BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
+  return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int blade_probe_qk(const void* q_tile, const void* k_tile, float* s_out, int32_t D, void* stream) {
+  return launch_probe(q_tile, k_tile, nullptr, s_out, D, 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int blade_probe_pv(const float* p_tile, const void* v_tile, float* o_out, int32_t D, void* stream) {
+  return launch_probe(nullptr, v_tile, p_tile, o_out, D, 1, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,227 @@
+// capi.cu -- C ABI glue: error state, device check, Gilbert tables (host), workspace carving and the
+// whole-layer entry point blade_asa_forward (AdaptiveBlockSparseAttnTrain.forward, W:383-408 / C:405-427).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace blade {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+size_t attn_park_bytes(int64_t D);
+int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
+                const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
+                int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Generalised Hilbert curve (the algorithm of gilbert3d.py:6-167), iterative, integer 3-vectors.
+// ---------------------------------------------------------------------------------------------
+struct V3 {
+  int x, y, z;
+};
+static inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+static inline int sgn(int v) { return (v > 0) - (v < 0); }
+static inline V3 sgn(V3 a) { return {sgn(a.x), sgn(a.y), sgn(a.z)}; }
+static inline int fdiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }  // floor(v/2)
+static inline V3 half(V3 a) { return {fdiv2(a.x), fdiv2(a.y), fdiv2(a.z)}; }
+static inline int mag(V3 a) { return abs(a.x + a.y + a.z); }
+
+struct Box {
+  V3 p, a, b, c;
+};
+
+static void gilbert_fill(int W, int H, int D, int64_t* curve2raster) {
+  std::vector<Box> stack;
+  const V3 o{0, 0, 0}, ex{W, 0, 0}, ey{0, H, 0}, ez{0, 0, D};
+  if (W >= H && W >= D) stack.push_back({o, ex, ey, ez});
+  else if (H >= W && H >= D) stack.push_back({o, ey, ex, ez});
+  else stack.push_back({o, ez, ex, ey});
+  int64_t n = 0;
+  auto emit_run = [&](V3 p, V3 d, int len) {
+    for (int i = 0; i < len; ++i) {
+      curve2raster[n++] = p.x + static_cast<int64_t>(W) * (p.y + static_cast<int64_t>(H) * p.z);
+      p = p + d;
+    }
+  };
+  while (!stack.empty()) {
+    const Box bx = stack.back();
+    stack.pop_back();
+    const V3 p = bx.p, a = bx.a, b = bx.b, c = bx.c;
+    const int w = mag(a), h = mag(b), d = mag(c);
+    const V3 da = sgn(a), db = sgn(b), dc = sgn(c);
+    if (h == 1 && d == 1) { emit_run(p, da, w); continue; }
+    if (w == 1 && d == 1) { emit_run(p, db, h); continue; }
+    if (w == 1 && h == 1) { emit_run(p, dc, d); continue; }
+    V3 a2 = half(a), b2 = half(b), c2 = half(c);
+    const int w2 = mag(a2), h2 = mag(b2), d2 = mag(c2);
+    if ((w2 % 2) && w > 2) a2 = a2 + da;
+    if ((h2 % 2) && h > 2) b2 = b2 + db;
+    if ((d2 % 2) && d > 2) c2 = c2 + dc;
+    Box kids[5];
+    int nk = 0;
+    if (2 * w > 3 * h && 2 * w > 3 * d) {
+      kids[nk++] = {p, a2, b, c};
+      kids[nk++] = {p + a2, a - a2, b, c};
+    } else if (3 * h > 4 * d) {
+      kids[nk++] = {p, b2, c, a2};
+      kids[nk++] = {p + b2, a, b - b2, c};
+      kids[nk++] = {p + (a - da) + (b2 - db), -b2, c, -(a - a2)};
+    } else if (3 * d > 4 * h) {
+      kids[nk++] = {p, c2, a2, b};
+      kids[nk++] = {p + c2, a, b, c - c2};
+      kids[nk++] = {p + (a - da) + (c2 - dc), -c2, -(a - a2), b};
+    } else {
+      kids[nk++] = {p, b2, c2, a2};
+      kids[nk++] = {p + b2, c, a2, b - b2};
+      kids[nk++] = {p + (b2 - db) + (c - dc), a, -b2, -(c - c2)};
+      kids[nk++] = {p + (a - da) + b2 + (c - dc), -c, -(a - a2), b - b2};
+      kids[nk++] = {p + (a - da) + (b2 - db), -b2, c2, -(a - a2)};
+    }
+    for (int i = nk - 1; i >= 0; --i) stack.push_back(kids[i]);
+  }
+}
+
+// workspace carving for blade_asa_forward
+struct ForwardWs {
+  size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, total;
+};
+static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg) {
+  ForwardWs w{};
+  const int64_t blk = cfg->block_size > 0 ? cfg->block_size : 128;
+  const int64_t nb = ceil_div(S, blk);
+  const int64_t np = cfg->sample_gap > 0 ? ceil_div(S, cfg->sample_gap) : 0;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.q_r = take(B * H * S * D * 2);
+  w.k_r = take(B * H * S * D * 2);
+  w.v_r = take(B * H * S * D * 2);
+  w.q_mean = take(B * H * nb * D * 4);
+  w.k_mean = take(B * H * nb * D * 4);
+  w.k_pool = take(B * H * (np > 0 ? np : 1) * D * 2);
+  w.v_pool = take(B * H * (np > 0 ? np : 1) * D * 2);
+  w.scores = take(B * H * nb * nb * 4);
+  w.idx = take(B * H * nb * nb * 4);
+  w.cnt = take(B * H * nb * 4);
+  w.park = take(attn_park_bytes(D));
+  w.total = off;
+  return w;
+}
+
+}  // namespace blade
+
+using namespace blade;
+
+extern "C" int blade_abi_version(void) { return BLADE_ABI_VERSION; }
+extern "C" const char* blade_last_error(void) { return last_error_buf(); }
+
+extern "C" int blade_device_check(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(BLADE_ERR_NO_DEVICE, "no CUDA device (%s); blade_asa has no CPU path", cudaGetErrorString(e));
+  }
+  int dev = 0, major = 0;
+  BLADE_CUDA_OK(cudaGetDevice(&dev));
+  BLADE_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  BLADE_REQUIRE(major == 10, BLADE_ERR_NO_DEVICE, "device compute capability %d.x is not sm_100", major);
+  return BLADE_OK;
+}
+
+extern "C" int blade_gilbert_tables(int32_t width, int32_t height, int32_t depth, int64_t* curve2raster,
+                                    int64_t* raster2curve) {
+  BLADE_REQUIRE(width >= 1 && height >= 1 && depth >= 1, BLADE_ERR_ARG, "grid dims must be >= 1");
+  BLADE_REQUIRE(curve2raster, BLADE_ERR_ARG, "curve2raster null");
+  const int64_t n = static_cast<int64_t>(width) * height * depth;
+  gilbert_fill(width, height, depth, curve2raster);
+  if (raster2curve)
+    for (int64_t c = 0; c < n; ++c) raster2curve[curve2raster[c]] = c;
+  return BLADE_OK;
+}
+
+extern "C" size_t blade_asa_workspace_bytes(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg) {
+  if (!cfg) return 0;
+  return carve(B, H, S, D, cfg).total;
+}
+
+extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                 const int32_t* src_row, const int32_t* dst_row, const BladeAsaConfig* cfg,
+                                 const float* scores_in, BladeTensor* out, float* scores_out, uint8_t* mask_out,
+                                 int32_t* idx_out, int32_t* cnt_out, void* workspace, size_t ws_bytes,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(cfg, BLADE_ERR_ARG, "cfg null");
+  if (int e = check_tensor16(q, "q")) return e;
+  BLADE_REQUIRE(cfg->block_size == 128, BLADE_ERR_ARG,
+                "blade_asa_forward: attention block size is 128 (W:325); got %d", cfg->block_size);
+  BLADE_REQUIRE(cfg->estimator == 0 || scores_in, BLADE_ERR_ARG, "estimator %d not available in this entry point",
+                cfg->estimator);
+  const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
+  const ForwardWs w = carve(B, H, S, D, cfg);
+  BLADE_REQUIRE(workspace && ws_bytes >= w.total, BLADE_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+                w.total, ws_bytes);
+  BLADE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, BLADE_ERR_ALIGN, "workspace must be 1 KiB aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int64_t nb = ceil_div(S, cfg->block_size);
+  const int64_t np = cfg->sample_gap > 0 ? ceil_div(S, cfg->sample_gap) : 0;
+  const bool rearr = src_row != nullptr;
+  float* q_mean = reinterpret_cast<float*>(ws + w.q_mean);
+  float* k_mean = reinterpret_cast<float*>(ws + w.k_mean);
+  float* scores = scores_out ? scores_out : reinterpret_cast<float*>(ws + w.scores);
+  int32_t* idx = idx_out ? idx_out : reinterpret_cast<int32_t*>(ws + w.idx);
+  int32_t* cnt = cnt_out ? cnt_out : reinterpret_cast<int32_t*>(ws + w.cnt);
+
+  const bool need_means = scores_in == nullptr;
+  if (int e = blade_asa_prep(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
+                             rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr,
+                             need_means ? k_mean : nullptr, np ? ws + w.k_pool : nullptr,
+                             np ? ws + w.v_pool : nullptr, cfg->block_size, cfg->sample_gap, stream))
+    return e;
+  const float* sc = scores_in;
+  if (!sc) {
+    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, stream)) return e;
+    sc = scores;
+  } else if (scores_out) {
+    BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, stream)) return e;
+
+  BladeTensor qr = *q, kr = *k, vr = *v;
+  if (rearr) {
+    const int64_t cs[4] = {H * S * D, S * D, D, 1};
+    qr.ptr = ws + w.q_r;
+    kr.ptr = ws + w.k_r;
+    vr.ptr = ws + w.v_r;
+    for (int i = 0; i < 4; ++i) qr.stride[i] = kr.stride[i] = vr.stride[i] = cs[i];
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  if (np) {
+    BladeTensor kp{}, vp{};
+    kp.ptr = ws + w.k_pool;
+    vp.ptr = ws + w.v_pool;
+    const int64_t ps[4] = {H * np * D, np * D, D, 1};
+    const int64_t sh[4] = {B, H, np, D};
+    for (int i = 0; i < 4; ++i) {
+      kp.shape[i] = vp.shape[i] = sh[i];
+      kp.stride[i] = vp.stride[i] = ps[i];
+    }
+    kp.dtype = vp.dtype = q->dtype;
+    return launch_attn(&qr, &kr, &vr, idx, cnt, nb, &kp, &vp, cfg->sample_gap, out, nullptr, dst_row, scale,
+                       cfg->exact_merge, ws + w.park, attn_park_bytes(D), stream);
+  }
+  return launch_attn(&qr, &kr, &vr, idx, cnt, nb, nullptr, nullptr, 0, out, nullptr, dst_row, scale, 0, ws + w.park,
+                     attn_park_bytes(D), stream);
+}

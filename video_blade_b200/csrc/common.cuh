@@ -1,0 +1,53 @@
+// common.cuh -- host-side error plumbing and small shared helpers for the blade_asa C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/blade_asa.h"
+
+namespace blade {
+
+char* last_error_buf();  // thread-local, 512 bytes (defined in capi.cu)
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define BLADE_CUDA_OK(expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::blade::fail(BLADE_ERR_LAUNCH, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define BLADE_REQUIRE(cond, code, ...) \
+  do {                                 \
+    if (!(cond)) return ::blade::fail(code, __VA_ARGS__); \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// validates a [B,H,S,D] 16-bit tensor for the vectorised / TMA paths
+inline int check_tensor16(const BladeTensor* t, const char* name) {
+  BLADE_REQUIRE(t && t->ptr, BLADE_ERR_ARG, "%s: null tensor", name);
+  BLADE_REQUIRE(t->dtype == BLADE_BF16 || t->dtype == BLADE_F16, BLADE_ERR_DTYPE,
+                "%s: dtype %d unsupported (bf16/f16 only)", name, t->dtype);
+  BLADE_REQUIRE(t->stride[3] == 1, BLADE_ERR_ALIGN, "%s: last dim must be contiguous", name);
+  BLADE_REQUIRE((reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0, BLADE_ERR_ALIGN, "%s: pointer not 16B aligned", name);
+  for (int i = 0; i < 3; ++i)
+    BLADE_REQUIRE((t->stride[i] * 2) % 16 == 0, BLADE_ERR_ALIGN, "%s: stride[%d]=%lld not 16B aligned", name, i,
+                  (long long)t->stride[i]);
+  BLADE_REQUIRE(t->shape[3] == 64 || t->shape[3] == 128, BLADE_ERR_SHAPE, "%s: head dim %lld not in {64,128}", name,
+                (long long)t->shape[3]);
+  return BLADE_OK;
+}
+
+}  // namespace blade

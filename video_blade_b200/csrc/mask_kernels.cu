@@ -1,0 +1,458 @@
+// mask_kernels.cu -- north-star kernel (a): mask generation for Adaptive Sparse Attention.
+//
+//   prep_block_kernel   HBM-bound: one pass over Q,K,V rows (optionally gathered into Gilbert-curve
+//                       order, W:142-152) producing curve-ordered copies and fp32 block means over the
+//                       replicate-padded sequence (W:25-36).  16-byte vector loads, a half-warp per 256-byte
+//                       row, 8 independent loads in flight per thread.
+//   pool_kernel         gap-means of K and V for the global branch (simple_pooling, W:88-93).
+//   score_meanpool_kernel  coarse nb x nb block-score GEMM on the means + row softmax (fp32).
+//   select_kernel       energy-threshold block selection (transfer_attn_to_mask, W:214-229 / C:228-248):
+//                       one warp per score row; stable descending order by rank counting, fp64 sequential
+//                       prefix sums rounded to fp32 (== torch CPU sort(stable)+cumsum, bit-exact),
+//                       ballot compaction into the ascending per-row block-index list.
+//   mask_to_index_kernel   bool mask -> the same index-list format.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace blade {
+
+template <bool IS_BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (IS_BF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 t = __half22float2(h);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+template <bool IS_BF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (IS_BF16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+struct Strides3 {
+  int64_t b, h, s;  // element strides
+};
+
+// ------------------------------------------------------------------------------------------------
+// prep: grid (nb, H, B), 256 threads.  One CTA = one block of `block` output rows of one head.
+// ------------------------------------------------------------------------------------------------
+template <int D, bool IS_BF16, bool COPY>
+__global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                         const uint16_t* __restrict__ v, Strides3 sq, Strides3 sk,
+                                                         Strides3 sv, const int32_t* __restrict__ src_row,
+                                                         uint16_t* __restrict__ q_r, uint16_t* __restrict__ k_r,
+                                                         uint16_t* __restrict__ v_r, float* __restrict__ q_mean,
+                                                         float* __restrict__ k_mean, int S, int H, int nb, int block) {
+  constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
+  constexpr int RPW = 32 / LPR;     // rows per warp-wide load
+  constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
+  constexpr int SLOTS = RPP;        // partial-sum slots
+  __shared__ float red[2][SLOTS][D];
+
+  const int blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, chunk = lane % LPR;
+  const int slot = warp * RPW + sub;
+  const int passes = block / RPP;   // host guarantees divisibility
+  const int row0 = blk * block;
+  const int64_t out_base = (static_cast<int64_t>(b) * H + h) * S;
+
+  float acc[2][8];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const uint16_t* src = t == 0 ? q : (t == 1 ? k : v);
+    const Strides3 st = t == 0 ? sq : (t == 1 ? sk : sv);
+    uint16_t* dst = t == 0 ? q_r : (t == 1 ? k_r : v_r);
+    if (t == 2 && !(COPY && dst != nullptr)) break;  // V is only needed for the copy
+    const uint16_t* base = src + b * st.b + h * st.h;
+    for (int p0 = 0; p0 < passes; p0 += 8) {
+      uint4 val[8];
+      int rows[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + u;
+        int r = row0 + p * RPP + slot;
+        rows[u] = r;
+        const int rc = r < S ? r : S - 1;  // replicate padding (W:35)
+        const int sr = src_row ? __ldg(src_row + rc) : rc;
+        if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (p0 + u >= passes) break;
+        if (COPY && dst != nullptr && rows[u] < S)
+          reinterpret_cast<uint4*>(dst + (out_base + rows[u]) * D)[chunk] = val[u];
+        if (t < 2) {
+          float f[8];
+          unpack8<IS_BF16>(val[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] += f[i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[t][slot][chunk * 8 + i] = acc[t][i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * D; e += 256) {
+    const int t = e / D, d = e % D;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) s += red[t][j][d];
+    float* dstm = t == 0 ? q_mean : k_mean;
+    if (dstm) dstm[((static_cast<int64_t>(b) * H + h) * nb + blk) * D + d] = s / static_cast<float>(block);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool: grid (ceil(np/8), H, B), 256 threads, one warp per pooled row.
+// ------------------------------------------------------------------------------------------------
+template <int D, bool IS_BF16>
+__global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ k, const uint16_t* __restrict__ v,
+                                                   Strides3 sk, Strides3 sv, const int32_t* __restrict__ src_row,
+                                                   uint16_t* __restrict__ k_pool, uint16_t* __restrict__ v_pool, int S,
+                                                   int H, int np, int gap) {
+  constexpr int LPR = D / 8;
+  constexpr int RPW = 32 / LPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + warp;
+  if (g >= np) return;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int sub = lane / LPR, chunk = lane % LPR;
+  const float inv = 1.0f / static_cast<float>(gap);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const uint16_t* base = (t == 0 ? k : v) + b * (t == 0 ? sk.b : sv.b) + h * (t == 0 ? sk.h : sv.h);
+    const int64_t ss = t == 0 ? sk.s : sv.s;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j0 = 0; j0 < gap; j0 += RPW * 4) {
+      uint4 val[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * RPW + sub;
+        ok[u] = j < gap;
+        int r = g * gap + j;
+        r = r < S ? r : S - 1;  // replicate padding (W:89 -> W:35)
+        const int sr = src_row ? __ldg(src_row + r) : r;
+        if (ok[u]) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * ss) + chunk);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float f[8];
+        unpack8<IS_BF16>(val[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= LPR; off >>= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    if (sub == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= inv;
+      uint16_t* dst = (t == 0 ? k_pool : v_pool) + ((static_cast<int64_t>(b) * H + h) * np + g) * D;
+      reinterpret_cast<uint4*>(dst)[chunk] = pack8<IS_BF16>(acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scores: grid (ceil(nb/8), B*H), 256 threads, one warp per score row.  dynamic smem: 8*(D + nb) floats
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
+                                                             float* __restrict__ scores, int nb, int D, float scale) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sq = sm + warp * (D + nb);
+  float* srow = sq + D;
+  const int i = blockIdx.x * 8 + warp;
+  const int64_t bh = blockIdx.y;
+  if (i >= nb) return;
+  const float* qrow = qm + (bh * nb + i) * D;
+  for (int d = lane; d < D; d += 32) sq[d] = qrow[d];
+  __syncwarp();
+  const float* kb = km + bh * nb * D;
+  float mx = -INFINITY;
+  for (int j = lane; j < nb; j += 32) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + static_cast<int64_t>(j) * D);
+    float dot = 0.f;
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 kv = __ldg(kr + d4);
+      dot = fmaf(sq[4 * d4 + 0], kv.x, dot);
+      dot = fmaf(sq[4 * d4 + 1], kv.y, dot);
+      dot = fmaf(sq[4 * d4 + 2], kv.z, dot);
+      dot = fmaf(sq[4 * d4 + 3], kv.w, dot);
+    }
+    dot *= scale;
+    srow[j] = dot;
+    mx = fmaxf(mx, dot);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.f;
+  for (int j = lane; j < nb; j += 32) {
+    const float e = expf(srow[j] - mx);
+    srow[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.0f / sum;
+  float* out = scores + (bh * nb + i) * nb;
+  for (int j = lane; j < nb; j += 32) out[j] = srow[j] * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: grid ceil(rows/8), 256 threads, one warp per score row.  dynamic smem: 8 * 2 * nk_pad floats
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int64_t total_rows, int nq, int nk,
+                                                     int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
+                                                     const int32_t* __restrict__ hi_bh, float thr, int force_last,
+                                                     int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
+                                                     uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk_pad = (nk + 31) & ~31;
+  float* vals = sm + warp * 2 * nk_pad;
+  float* sorted = vals + nk_pad;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= total_rows) return;
+  const int qi = static_cast<int>(row % nq);
+  const int64_t bh = row / nq;
+  const float* src = scores + row * nk;
+  for (int j = lane; j < nk_pad; j += 32) vals[j] = j < nk ? src[j] : -INFINITY;
+  __syncwarp();
+
+  // rank of element j under (value desc, index asc): #{i : v_i > v_j or (v_i == v_j and i < j)}
+  const int nslot = nk_pad / 32;
+  for (int s = 0; s < nslot; ++s) {
+    const int j = s * 32 + lane;
+    const float vj = vals[j];
+    int rank = 0;
+    for (int i = 0; i < nk; ++i) {
+      const float vi = vals[i];  // warp-uniform address: smem broadcast
+      rank += (vi > vj) || (vi == vj && i < j);
+    }
+    if (j < nk) sorted[rank] = vj;
+    // stash the rank where the value was (vals no longer needed for this j after the loop? other lanes
+    // still read vals[j] in later slots, so ranks go to registers via a second pass below)
+  }
+  __syncwarp();
+
+  // fp64 sequential prefix sums, each prefix rounded to fp32 (torch.cumsum on CPU); find the cut.
+  int kfirst = nk;
+  if (lane == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < nk; ++i) acc += static_cast<double>(sorted[i]);
+    const float total = static_cast<float>(acc);
+    const float th = __fmul_rn(thr, total);
+    acc = 0.0;
+    for (int i = 0; i < nk; ++i) {
+      acc += static_cast<double>(sorted[i]);
+      if (static_cast<float>(acc) >= th) {
+        kfirst = i;
+        break;
+      }
+    }
+  }
+  kfirst = __shfl_sync(0xffffffffu, kfirst, 0);
+  const int lo = lo_bh ? lo_bh[bh] : lo_s;
+  const int hi = hi_bh ? hi_bh[bh] : hi_s;
+  int kc = kfirst < lo ? lo : kfirst;
+  kc = kc > hi ? hi : kc;
+  if (kcut && lane == 0) kcut[row] = kc;
+
+  const bool full_row = force_last > 0 && qi >= nq - force_last;
+  int32_t* irow = idx + row * nk;
+  uint8_t* mrow = mask ? mask + row * nk : nullptr;
+  int base = 0;
+  for (int s = 0; s < nslot; ++s) {
+    const int j = s * 32 + lane;
+    const float vj = vals[j];
+    int rank = 0;
+    for (int i = 0; i < nk; ++i) {
+      const float vi = vals[i];
+      rank += (vi > vj) || (vi == vj && i < j);
+    }
+    bool sel = j < nk && (rank < kc || full_row || (force_last > 0 && j >= nk - force_last));
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    if (sel) irow[base + __popc(bal & ((1u << lane) - 1u))] = j;
+    if (mrow && j < nk) mrow[j] = sel ? 1 : 0;
+    base += __popc(bal);
+  }
+  for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
+  if (lane == 0) cnt[row] = base;
+}
+
+__global__ void __launch_bounds__(256) mask_to_index_kernel(const uint8_t* __restrict__ mask, int64_t total_rows, int nk,
+                                                            int32_t* __restrict__ idx, int32_t* __restrict__ cnt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= total_rows) return;
+  const uint8_t* mrow = mask + row * nk;
+  int32_t* irow = idx + row * nk;
+  int base = 0;
+  for (int j0 = 0; j0 < nk; j0 += 32) {
+    const int j = j0 + lane;
+    const bool sel = j < nk && mrow[j] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    if (sel) irow[base + __popc(bal & ((1u << lane) - 1u))] = j;
+    base += __popc(bal);
+  }
+  for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
+  if (lane == 0) cnt[row] = base;
+}
+
+}  // namespace blade
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace blade;
+
+extern "C" int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row,
+                              void* q_r, void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool,
+                              void* v_pool, int32_t block_size, int32_t sample_gap, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_tensor16(q, "q")) return e;
+  if (int e = check_tensor16(k, "k")) return e;
+  if (int e = check_tensor16(v, "v")) return e;
+  const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
+  for (int i = 0; i < 4; ++i)
+    BLADE_REQUIRE(k->shape[i] == q->shape[i] && v->shape[i] == q->shape[i], BLADE_ERR_SHAPE,
+                  "q/k/v shapes differ in dim %d (reference asserts equality, W:250-251)", i);
+  BLADE_REQUIRE(q->dtype == k->dtype && q->dtype == v->dtype, BLADE_ERR_DTYPE, "q/k/v dtypes differ");
+  BLADE_REQUIRE(block_size == 64 || block_size == 128, BLADE_ERR_ARG, "block_size %d not in {64,128}", block_size);
+  BLADE_REQUIRE(S >= 1 && B >= 1 && H >= 1 && H <= 65535 && B <= 65535, BLADE_ERR_SHAPE, "bad B/H/S");
+  const bool copy = q_r || k_r || v_r;
+  BLADE_REQUIRE(!copy || (q_r && k_r && v_r), BLADE_ERR_ARG, "q_r/k_r/v_r must be all set or all NULL");
+  BLADE_REQUIRE(copy || !src_row, BLADE_ERR_ARG, "src_row given but no output copies requested");
+  const int nb = static_cast<int>(ceil_div(S, block_size));
+  const bool bf = q->dtype == BLADE_BF16;
+  Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
+      sv{v->stride[0], v->stride[1], v->stride[2]};
+  const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
+                 *vp = static_cast<const uint16_t*>(v->ptr);
+  if (q_mean || k_mean || copy) {
+    dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
+#define LAUNCH_PREP(DD, BF, CP)                                                                                   \
+  prep_block_kernel<DD, BF, CP><<<grid, 256, 0, stream>>>(qp, kp, vp, sq, sk, sv, src_row,                        \
+                                                          static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
+                                                          static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
+                                                          static_cast<int>(S), static_cast<int>(H), nb, block_size)
+    if (D == 128) {
+      if (bf) { if (copy) LAUNCH_PREP(128, true, true); else LAUNCH_PREP(128, true, false); }
+      else    { if (copy) LAUNCH_PREP(128, false, true); else LAUNCH_PREP(128, false, false); }
+    } else {
+      if (bf) { if (copy) LAUNCH_PREP(64, true, true); else LAUNCH_PREP(64, true, false); }
+      else    { if (copy) LAUNCH_PREP(64, false, true); else LAUNCH_PREP(64, false, false); }
+    }
+#undef LAUNCH_PREP
+    BLADE_CUDA_OK(cudaGetLastError());
+  }
+  if (sample_gap > 0 && k_pool && v_pool) {
+    const int np = static_cast<int>(ceil_div(S, sample_gap));
+    // read the curve-ordered copies when they exist (contiguous, no gather), else the sources
+    const uint16_t* ks = copy ? static_cast<const uint16_t*>(k_r) : kp;
+    const uint16_t* vs = copy ? static_cast<const uint16_t*>(v_r) : vp;
+    Strides3 ck{H * S * D, S * D, D};
+    Strides3 pk = copy ? ck : sk, pv = copy ? ck : sv;
+    const int32_t* sr = copy ? nullptr : src_row;
+    dim3 grid(static_cast<unsigned>(ceil_div(np, 8)), static_cast<unsigned>(H), static_cast<unsigned>(B));
+#define LAUNCH_POOL(DD, BF)                                                                                      \
+  pool_kernel<DD, BF><<<grid, 256, 0, stream>>>(ks, vs, pk, pv, sr, static_cast<uint16_t*>(k_pool),             \
+                                                static_cast<uint16_t*>(v_pool), static_cast<int>(S),            \
+                                                static_cast<int>(H), np, sample_gap)
+    if (D == 128) { if (bf) LAUNCH_POOL(128, true); else LAUNCH_POOL(128, false); }
+    else          { if (bf) LAUNCH_POOL(64, true); else LAUNCH_POOL(64, false); }
+#undef LAUNCH_POOL
+    BLADE_CUDA_OK(cudaGetLastError());
+  }
+  return BLADE_OK;
+}
+
+extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores, int64_t B, int64_t H,
+                                         int64_t nb, int64_t D, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(q_mean && k_mean && scores, BLADE_ERR_ARG, "null pointer");
+  BLADE_REQUIRE(D % 4 == 0 && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
+  const size_t smem = 8 * (D + nb) * sizeof(float);
+  BLADE_REQUIRE(smem <= 200 * 1024, BLADE_ERR_SHAPE, "nb too large for score kernel");
+  if (smem > 48 * 1024)
+    BLADE_CUDA_OK(cudaFuncSetAttribute(score_meanpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(static_cast<unsigned>(ceil_div(nb, 8)), static_cast<unsigned>(B * H));
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  score_meanpool_kernel<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, (int)D, scale);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64_t nq, int64_t nk,
+                                const BladeAsaConfig* cfg, const int32_t* lo_bh, const int32_t* hi_bh, int32_t* idx,
+                                int32_t* cnt, uint8_t* mask_opt, int32_t* kcut_opt, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(scores && idx && cnt && cfg, BLADE_ERR_ARG, "null pointer");
+  BLADE_REQUIRE(nq >= 1 && nk >= 1 && nk <= 4096, BLADE_ERR_SHAPE, "bad nq/nk");
+  BLADE_REQUIRE(cfg->min_retain >= 1 && cfg->max_retain >= 1, BLADE_ERR_ARG, "retain bounds must be >= 1");
+  const int64_t rows = B * H * nq;
+  const int nk_pad = static_cast<int>((nk + 31) & ~31);
+  const size_t smem = 8 * 2 * nk_pad * sizeof(float);
+  if (smem > 48 * 1024)
+    BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
+      scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
+      cfg->force_last, idx, cnt, mask_opt, kcut_opt);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+extern "C" int blade_mask_to_index(const uint8_t* mask, int64_t B, int64_t H, int64_t nq, int64_t nk, int32_t* idx,
+                                   int32_t* cnt, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(mask && idx && cnt, BLADE_ERR_ARG, "null pointer");
+  const int64_t rows = B * H * nq;
+  mask_to_index_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, stream>>>(mask, rows, (int)nk, idx, cnt);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
