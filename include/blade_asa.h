@@ -148,6 +148,12 @@ int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTen
                       int32_t* idx_out, int32_t* cnt_out,
                       void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- measurement hook ------------------------------------------------------------------------
+ * When set, the library records the given cudaEvent_t pair (passed as void*) on the caller's stream
+ * immediately before / after the launches of one stage, so a harness can time a kernel INSIDE a whole-layer
+ * call.  stage: 0 = prep (+pool), 1 = scores, 2 = select, 3 = attention.  NULL,NULL clears the slot. */
+int blade_profile_events(int32_t stage, void* start_event, void* stop_event);
+
 /* ---- bring-up probes (tests only): single-tile tcgen05 GEMMs dumped from TMEM --------------- */
 int blade_probe_qk(const void* q_tile /*bf16 [128,D]*/, const void* k_tile /*bf16 [128,D]*/,
                    float* s_out /*[128,128]*/, int32_t D, void* stream);

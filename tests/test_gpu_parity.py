@@ -1,0 +1,309 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle.
+
+Gates (BASELINE.json north_star): block mask / index list bit-exact given the same fp32 scores;
+attention output rel-L2 <= 1e-2 and max-abs <= 2e-2 given the same inputs and mask."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bf16_from_bits, load_npz
+from oracle import asa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_L2, MAX_ABS = 1e-2, 2e-2
+
+
+def _engine(**kw):
+    from video_blade_b200.asa import AsaEngine, AsaKnobs
+    flavor = kw.pop("flavor", "wan")
+    kn = AsaKnobs.cog(**kw) if flavor == "cog" else AsaKnobs.wan(**kw)
+    return AsaEngine(kn)
+
+
+def _close(got, want, rel=REL_L2, mx=MAX_ABS):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert not torch.isnan(got).any()
+    d = got - want
+    r = float(d.norm() / want.norm().clamp_min(1e-30))
+    m = float(d.abs().max())
+    assert r <= rel and m <= mx, (r, m)
+    return r, m
+
+
+# ------------------------------------------------------------------ tcgen05 bring-up probes
+@pytest.mark.parametrize("D", [64, 128])
+def test_probe_umma_descriptors(D):
+    from video_blade_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(D)
+    q = torch.randn(128, D, generator=g).bfloat16().cuda()
+    k = torch.randn(128, D, generator=g).bfloat16().cuda()
+    s = torch.zeros(128, 128, device="cuda")
+    _lib.check(lib.blade_probe_qk(q.data_ptr(), k.data_ptr(), s.data_ptr(), D, _lib.current_stream()))
+    p = torch.rand(128, 128, generator=g).cuda()
+    v = torch.randn(128, D, generator=g).bfloat16().cuda()
+    o = torch.zeros(128, D, device="cuda")
+    _lib.check(lib.blade_probe_pv(p.data_ptr(), v.data_ptr(), o.data_ptr(), D, _lib.current_stream()))
+    torch.cuda.synchronize()
+    _close(s, q.float() @ k.float().T, 1e-5, 1e-3)
+    _close(o, p.bfloat16().float() @ v.float(), 1e-5, 1e-3)
+
+
+# ------------------------------------------------------------------ selection: bit-exact
+def test_select_golden_reference_cases():
+    """scores -> mask produced by the REFERENCE's transfer_attn_to_mask (tests/golden/select_cases.npz)."""
+    z, meta = load_npz("select_cases.npz")
+    for m in meta:
+        c, nb = m["case"], m["nb"]
+        sc = torch.from_numpy(z[f"scores_{c}"])
+        want = torch.from_numpy(np.unpackbits(z[f"mask_{c}"], axis=-1)[..., :nb].astype(bool))
+        eng = _engine(flavor=m["flavor"])
+        lo, hi = O.retain_bounds(nb, m["min_ratio"], m["max_ratio"], m["flavor"])
+        idx, cnt, mask = eng.select(sc.cuda(), lo=lo, hi=hi, force_last=2 if m["flavor"] == "cog" else 0,
+                                    thr=m["thr"])
+        assert torch.equal(mask.cpu(), want), m
+        widx, wcnt = O.mask_to_index_list(want)
+        assert torch.equal(idx.cpu(), widx) and torch.equal(cnt.cpu(), wcnt), m
+
+
+@pytest.mark.parametrize("nb", [61, 122, 139, 256])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_select_bit_exact_vs_oracle(nb, seed):
+    g = torch.Generator().manual_seed(seed * 1000 + nb)
+    kinds = [torch.softmax(torch.randn(1, 3, nb, nb, generator=g) * 3.0, -1),
+             (torch.randint(0, 5, (1, 3, nb, nb), generator=g).float() + 1) / 7.0,      # exact ties everywhere
+             torch.softmax(torch.randn(1, 3, nb, nb, generator=g) * 0.05, -1)]          # saturates max_retain
+    for sc in kinds:
+        for flavor in ("wan", "cog"):
+            lo, hi = O.retain_bounds(nb, 0.05, 0.17 if flavor == "wan" else 0.1, flavor)
+            force = 2 if flavor == "cog" else 0
+            want, wk = O.select_blocks_energy(sc, lo, hi, 0.95, force_last=force)
+            eng = _engine(flavor=flavor)
+            idx, cnt, mask = eng.select(sc.cuda(), lo=lo, hi=hi, force_last=force)
+            assert torch.equal(mask.cpu(), want)
+            widx, wcnt = O.mask_to_index_list(want)
+            assert torch.equal(idx.cpu(), widx) and torch.equal(cnt.cpu(), wcnt)
+
+
+def test_select_edge_cases():
+    eng = _engine()
+    # one block only; all-equal scores; a row with a single dominant block; nk not a multiple of 32
+    for nb in (1, 2, 33):
+        sc = torch.full((1, 1, nb, nb), 1.0 / nb)
+        want, _ = O.select_blocks_energy(sc, 1, max(1, nb // 2), 0.95)
+        _, _, mask = eng.select(sc.cuda(), lo=1, hi=max(1, nb // 2), force_last=0)
+        assert torch.equal(mask.cpu(), want)
+    sc = torch.zeros(1, 1, 40, 40)
+    sc[..., 7] = 1.0
+    want, _ = O.select_blocks_energy(sc, 2, 6, 0.95)
+    _, _, mask = eng.select(sc.cuda(), lo=2, hi=6, force_last=0)
+    assert torch.equal(mask.cpu(), want)
+
+
+def test_mask_to_index_roundtrip():
+    eng = _engine()
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(2, 3, 37, 53, generator=g) < 0.3
+    idx, cnt = eng.mask_to_index(mask.cuda())
+    widx, wcnt = O.mask_to_index_list(mask)
+    assert torch.equal(idx.cpu(), widx) and torch.equal(cnt.cpu(), wcnt)
+
+
+# ------------------------------------------------------------------ prep / pooling / scores
+@pytest.mark.parametrize("flavor,grid,T,H,D", [("wan", (26, 15, 4), 0, 2, 128), ("cog", (15, 10, 6), 40, 3, 64),
+                                               ("wan", (8, 6, 4), 0, 1, 128)])
+def test_prep_gather_means_pool(flavor, grid, T, H, D):
+    S = grid[0] * grid[1] * grid[2] + T
+    gap = 30 if flavor == "wan" else 15
+    eng = _engine(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, sample_gap=gap)
+    q, k, v = O.synth_qkv(2, H, S, D, seed=5)
+    # strided inputs, as the processor passes them
+    qc, kc, vc = (x.transpose(1, 2).contiguous().cuda().transpose(1, 2) for x in (q, k, v))
+    (qr, kr, vr), (qm, km), (kp, vp) = eng.prep(qc, kc, vc, rearrange=True)
+    rr = O.GilbertRearranger(*grid, text_length=T)
+    assert torch.equal(qr.cpu(), rr.rearrange(q)) and torch.equal(kr.cpu(), rr.rearrange(k))
+    assert torch.equal(vr.cpu(), rr.rearrange(v))
+    qp = O.pad_to_multiple(rr.rearrange(q), 128).float()
+    nb = qp.size(2) // 128
+    _close(qm, qp.reshape(2, H, nb, 128, D).mean(3), 1e-5, 1e-5)
+    _close(kp, O.simple_pooling(rr.rearrange(k), gap), 3e-3, 8e-3)          # bf16 rounding of a different fp32 sum order
+    _close(vp, O.simple_pooling(rr.rearrange(v), gap), 3e-3, 8e-3)
+    sc = eng.scores_meanpool(qm, km)
+    _close(sc, O.estimator_meanpool(rr.rearrange(q), rr.rearrange(k), 128), 1e-4, 1e-5)
+    # no rearrangement: pooled/means straight from the strided source
+    (a, b, c), (qm2, _), (kp2, _) = eng.prep(qc, kc, vc, rearrange=False)
+    assert a is None
+    _close(qm2, O.pad_to_multiple(q, 128).float().reshape(2, H, nb, 128, D).mean(3), 1e-5, 1e-5)
+    _close(kp2, O.simple_pooling(k, gap), 3e-3, 8e-3)
+
+
+# ------------------------------------------------------------------ attention
+def _rand_mask(B, H, nq, nk, density, seed):
+    g = torch.Generator().manual_seed(seed)
+    m = torch.rand(B, H, nq, nk, generator=g) < density
+    m[..., 0] = True                       # every row keeps at least one block
+    m[:, :, -1, -1] = True                 # and the ragged tail block is exercised
+    return m
+
+
+@pytest.mark.parametrize("D,H,S", [(128, 2, 1560), (64, 3, 940), (128, 1, 128), (128, 1, 1024), (64, 2, 300),
+                                   (128, 3, 129)])
+def test_block_sparse_attn_vs_oracle(D, H, S):
+    eng = _engine(use_rearrange=False)
+    q, k, v = O.synth_qkv(1, H, S, D, seed=S)
+    nb = -(-S // 128)
+    mask = _rand_mask(1, H, nb, nb, 0.4, seed=S + 1)
+    idx, cnt = O.mask_to_index_list(mask)
+    out, lse = eng.block_sparse_attn(q.cuda(), k.cuda(), v.cuda(), idx.cuda(), cnt.cuda())
+    wout, wlse = O.dense_masked_attention(q, k, v, mask)
+    _close(out, wout)
+    _close(lse, wlse, 1e-5, 1e-4)
+
+
+def test_block_sparse_attn_dense_mask_batch2_strided():
+    """all-ones mask == plain attention (the reference's standard_attn, W:21-24); B=2; strided q/k/v."""
+    eng = _engine(use_rearrange=False)
+    q, k, v = O.synth_qkv(2, 2, 700, 128, seed=11)
+    qc, kc, vc = (x.transpose(1, 2).contiguous().cuda().transpose(1, 2) for x in (q, k, v))
+    nb = 6
+    mask = torch.ones(2, 2, nb, nb, dtype=torch.bool)
+    idx, cnt = eng.mask_to_index(mask.cuda())
+    out, lse = eng.block_sparse_attn(qc, kc, vc, idx, cnt)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    _close(out, ref.to(q.dtype))
+
+
+@pytest.mark.parametrize("flavor,D,H,S,gap", [("wan", 128, 2, 1560, 30), ("cog", 64, 3, 940, 15), ("wan", 128, 1, 4000, 30)])
+def test_asa_attn_pooled_merge_vs_oracle(flavor, D, H, S, gap):
+    eng = _engine(flavor=flavor, use_rearrange=False, sample_gap=gap)
+    q, k, v = O.synth_qkv(1, H, S, D, seed=S + 7, structured=1.5, grid=(S // 20, 10, 2))
+    nb = -(-S // 128)
+    mask = _rand_mask(1, H, nb, nb, 0.3, seed=S + 2)
+    idx, cnt = O.mask_to_index_list(mask)
+    kp, vp = O.simple_pooling(k, gap), O.simple_pooling(v, gap)
+    out = eng.asa_attn(q.cuda(), k.cuda(), v.cuda(), idx.cuda(), cnt.cuda(), kp.cuda(), vp.cuda())
+    o1, l1 = O.dense_masked_attention(q, k, v, mask)
+    o2, l2 = O.standard_attn(q, kp, vp)
+    want = O.merge_lse(o1, l1.unsqueeze(-1).to(q.dtype), o2, l2.unsqueeze(-1).to(q.dtype), gap)
+    _close(out, want)
+
+
+# ------------------------------------------------------------------ the whole layer
+@pytest.mark.parametrize("name", ["layer_wan_small.npz", "layer_cog_small.npz"])
+def test_layer_vs_reference_golden(name):
+    """Output of the REFERENCE's AdaptiveBlockSparseAttnTrain.forward (golden) vs the CUDA layer fed the same
+    fp32 block scores (the reference estimator's, recomputed by the oracle from the recorded RNG seed)."""
+    z, m = load_npz(name)
+    q, k, v = (bf16_from_bits(z[n]) for n in ("q", "k", "v"))
+    flavor = "cog" if m["text_length"] else "wan"
+    w, h, d = m["grid"]
+    for use_rr, key in ((True, "out"), (False, "out_norearrange")):
+        want = bf16_from_bits(z[key])
+        cfg = O.ASAConfig(flavor=flavor, width=w, height=h, depth=d, text_length=m["text_length"],
+                          sample_gap=m["sample_gap"], max_retain_ratio=m["max_retain_ratio"],
+                          min_retain_ratio=m["min_retain_ratio"], estimator="sampled_max", use_rearrange=use_rr)
+        g = torch.Generator().manual_seed(m["rng_seed"])
+        B, H = q.shape[:2]
+        qo = O.draw_sample_offsets(B, H, 128, 32, g)
+        ko = O.draw_sample_offsets(B, H, 128, 32, g)
+        ref = O.asa_forward(q, k, v, cfg, qo, ko)
+        assert torch.equal(ref.out, want)
+        eng = _engine(flavor=flavor, width=w, height=h, depth=d, text_length=m["text_length"],
+                      sample_gap=m["sample_gap"], max_retain_ratio=m["max_retain_ratio"],
+                      min_retain_ratio=m["min_retain_ratio"], use_rearrange=use_rr)
+        out, dbg = eng.forward(q.cuda(), k.cuda(), v.cuda(), scores=ref.scores.float().cuda(), return_debug=True)
+        assert torch.equal(dbg["mask"].cpu(), ref.mask)
+        _close(out, want)
+
+
+@pytest.mark.parametrize("flavor", ["wan", "cog"])
+def test_layer_meanpool_end_to_end(flavor):
+    """mean-pool estimator path: mask bit-exact from the kernel's own scores; scores within fp32 tolerance;
+    output within bf16 tolerance of the oracle run on those scores."""
+    if flavor == "wan":
+        grid, T, H, D, gap, mr = (26, 15, 4), 0, 2, 128, 30, 0.4
+    else:
+        grid, T, H, D, gap, mr = (15, 10, 6), 40, 3, 64, 15, 0.3
+    S = grid[0] * grid[1] * grid[2] + T
+    q, k, v = O.synth_qkv(1, H, S, D, seed=9, structured=2.0, grid=grid, text_length=T)
+    eng = _engine(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, sample_gap=gap,
+                  max_retain_ratio=mr)
+    qc, kc, vc = (x.transpose(1, 2).contiguous().cuda().transpose(1, 2) for x in (q, k, v))
+    out, dbg = eng.forward(qc, kc, vc, return_debug=True)
+    cfg = O.ASAConfig(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, sample_gap=gap,
+                      max_retain_ratio=mr)
+    rr = O.GilbertRearranger(*grid, text_length=T)
+    want_sc = O.estimator_meanpool(rr.rearrange(q), rr.rearrange(k), 128)
+    _close(dbg["scores"], want_sc, 1e-4, 1e-5)
+    want_mask, _ = O.select_mask(dbg["scores"].cpu(), cfg)
+    assert torch.equal(dbg["mask"].cpu(), want_mask)
+    ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu())
+    _close(out, ref.out)
+    assert out.transpose(1, 2).is_contiguous()          # processor's transpose(1,2).flatten(2,3) is a view
+
+
+def test_drop_in_module_api():
+    """The mirror of the reference module: same names, knobs read at call time."""
+    from video_blade_b200 import wanx_blocksparseattn as W
+    W.width, W.height, W.depth, W.max_retain_ratio = 26, 15, 4, 0.4
+    try:
+        layer = W.AdaptiveBlockSparseAttnTrain()
+        layer.print_every = 0
+        S = 26 * 15 * 4
+        q, k, v = O.synth_qkv(1, 2, S, 128, seed=13, structured=2.0, grid=(26, 15, 4))
+        out = layer(q.cuda(), k.cuda(), v.cuda())
+        assert out.shape == q.shape and out.dtype == q.dtype
+        assert 0.0 < layer.average_sparsity() < 1.0
+        # block_sparse_attn(q,k,v,mask) -> (out, lse[B,H,S,1] in q.dtype), W:278-309
+        mask = _rand_mask(1, 2, 13, 13, 0.5, 1)
+        o, lse = W.block_sparse_attn(q.cuda(), k.cuda(), v.cuda(), mask.cuda())
+        wo, wl = O.dense_masked_attention(q, k, v, mask)
+        _close(o, wo)
+        assert lse.shape == (1, 2, S, 1) and lse.dtype == q.dtype
+        m = W.transfer_attn_to_mask(torch.softmax(torch.randn(1, 2, 61, 61), -1).cuda(), max_retain_ratio=0.17,
+                                    min_retain_ratio=0.05)
+        assert m.dtype == torch.bool and m.shape == (1, 2, 61, 61)
+        with pytest.raises(ValueError):
+            W.transfer_attn_to_mask(m.float(), mode="bogus")
+    finally:
+        W.width, W.height, W.depth, W.max_retain_ratio = 52, 30, 21, 0.17
+
+
+def test_full_size_wan_head_properties():
+    """BASELINE size (32760 tokens) through size-independent properties: (1) permutation equivariance --
+    running with use_rearrange on natural-order input == running without it on pre-permuted input;
+    (2) all-ones index list == dense attention (lse matches a chunked fp32 torch evaluation);
+    (3) linearity in V: out(v1+v2) ~= out(v1)+out(v2) for the block-sparse branch."""
+    from video_blade_b200.asa import AsaEngine, AsaKnobs
+    kn = AsaKnobs.wan()
+    S, H, D = 32760, 1, 128
+    q, k, v = O.synth_qkv(1, H, S, D, seed=21)
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    eng = AsaEngine(kn)
+    out, dbg = eng.forward(qc, kc, vc, return_debug=True)
+    src = eng.src_row(qc.device, S).long()
+    eng_nr = AsaEngine(AsaKnobs.wan(use_rearrange=False))
+    out_p, dbg_p = eng_nr.forward(qc[:, :, src].contiguous(), kc[:, :, src].contiguous(), vc[:, :, src].contiguous(),
+                                  return_debug=True)
+    assert torch.equal(dbg["mask"], dbg_p["mask"])
+    back = torch.empty_like(out_p)
+    back[:, :, src] = out_p
+    assert torch.equal(out, back)
+    # (3) linearity of the sparse branch in V
+    idx, cnt = dbg_p["idx"], dbg_p["cnt"]
+    v2 = torch.randn_like(vc)
+    qa, ka = qc[:, :, src].contiguous(), kc[:, :, src].contiguous()
+    o1, l1 = eng_nr.block_sparse_attn(qa, ka, vc, idx, cnt)
+    o2, l2 = eng_nr.block_sparse_attn(qa, ka, v2, idx, cnt)
+    o12, l12 = eng_nr.block_sparse_attn(qa, ka, vc + v2, idx, cnt)
+    assert torch.equal(l1, l2) and torch.equal(l1, l12)
+    _close(o12, o1.float() + o2.float(), 2e-2, 4e-2)
+    # (2) one q-block against a chunked fp32 evaluation of its selected blocks
+    i = 100
+    sel = idx[0, 0, i, : int(cnt[0, 0, i])].long()
+    cols = (sel[:, None] * 128 + torch.arange(128, device="cuda")[None]).reshape(-1)
+    cols = cols[cols < S]
+    s = (qa[0, 0, i * 128:(i + 1) * 128].float() @ ka[0, 0, cols].float().T) / D ** 0.5
+    _close(l1[0, 0, i * 128:(i + 1) * 128], torch.logsumexp(s, -1), 1e-5, 1e-4)
+    _close(o1[0, 0, i * 128:(i + 1) * 128], torch.softmax(s, -1) @ vc[0, 0, cols].float())

@@ -1,0 +1,53 @@
+"""CPU, world_size 2 and 4 over gloo: the Ulysses head/sequence exchange is exact (layout logic only; the
+attention in the middle is a per-head stand-in so no GPU is needed)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _per_head_op(x):
+    """[1,S,h,D] -> [1,S,h,D]; depends on the whole sequence of each head (like attention does)."""
+    w = torch.softmax(x.float().mean(-1, keepdim=True), dim=1)
+    return (x.float() * w + x.float().flip(1).cumsum(1) * 1e-3).to(x.dtype)
+
+
+def _worker(rank, world, degree, port, S, H, D):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from video_blade_b200.ulysses import UlyssesGroup
+        ug = UlyssesGroup(world, rank, degree)
+        gid, pr = rank // degree, rank % degree
+        g = torch.Generator().manual_seed(100 + gid)            # one sequence per group
+        full = torch.randn(1, S, H, D, generator=g)
+        sl = slice(pr * (S // degree), (pr + 1) * (S // degree))
+        x = full[:, sl].contiguous()
+        xq, xk = ug.scatter_heads(x, x * 2)
+        Hl = H // degree
+        assert xq.shape == (1, S, Hl, D)
+        assert torch.equal(xq, full[:, :, pr * Hl:(pr + 1) * Hl])
+        assert torch.equal(xk, 2 * full[:, :, pr * Hl:(pr + 1) * Hl])
+        y = ug.gather_heads(_per_head_op(xq))
+        want = _per_head_op(full)[:, sl]
+        assert y.shape == want.shape and torch.equal(y, want)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,degree", [(2, 2), (4, 2), (4, 4)])
+def test_ulysses_roundtrip_gloo(world, degree):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, degree, port, 24, 12, 8), nprocs=world, join=True)

@@ -692,6 +692,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.exact_merge = exact_merge;
 
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
+  StageTimer timer(3, stream);
 #define LAUNCH_ATTN(DD, BF)                                                                                     \
   do {                                                                                                          \
     auto kern = asa_attn_kernel<DD, BF>;                                                                        \

@@ -14,6 +14,11 @@ char* last_error_buf() {
   return buf;
 }
 
+StageEvents* stage_events() {
+  static StageEvents ev[4] = {};
+  return ev;
+}
+
 size_t attn_park_bytes(int64_t D);
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
@@ -126,6 +131,13 @@ using namespace blade;
 
 extern "C" int blade_abi_version(void) { return BLADE_ABI_VERSION; }
 extern "C" const char* blade_last_error(void) { return last_error_buf(); }
+
+extern "C" int blade_profile_events(int32_t stage, void* start_event, void* stop_event) {
+  BLADE_REQUIRE(stage >= 0 && stage < 4, BLADE_ERR_ARG, "stage %d out of range", stage);
+  stage_events()[stage].start = static_cast<cudaEvent_t>(start_event);
+  stage_events()[stage].stop = static_cast<cudaEvent_t>(stop_event);
+  return BLADE_OK;
+}
 
 extern "C" int blade_device_check(void) {
   int n = 0;

@@ -32,6 +32,22 @@ inline int fail(int code, const char* fmt, ...) {
     if (!(cond)) return ::blade::fail(code, __VA_ARGS__); \
   } while (0)
 
+// optional profiling events (blade_profile_events): stage 0 prep, 1 scores, 2 select, 3 attention
+struct StageEvents {
+  cudaEvent_t start, stop;
+};
+StageEvents* stage_events();  // array of 4 (defined in capi.cu)
+struct StageTimer {
+  int stage;
+  cudaStream_t stream;
+  StageTimer(int s, cudaStream_t st) : stage(s), stream(st) {
+    if (stage_events()[stage].start) cudaEventRecord(stage_events()[stage].start, stream);
+  }
+  ~StageTimer() {
+    if (stage_events()[stage].stop) cudaEventRecord(stage_events()[stage].stop, stream);
+  }
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -372,6 +372,7 @@ extern "C" int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const 
   const bool bf = q->dtype == BLADE_BF16;
   Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
       sv{v->stride[0], v->stride[1], v->stride[2]};
+  StageTimer timer(0, stream);
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
   if (q_mean || k_mean || copy) {
@@ -421,6 +422,7 @@ extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mea
   BLADE_REQUIRE(smem <= 200 * 1024, BLADE_ERR_SHAPE, "nb too large for score kernel");
   if (smem > 48 * 1024)
     BLADE_CUDA_OK(cudaFuncSetAttribute(score_meanpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StageTimer timer(1, stream);
   dim3 grid(static_cast<unsigned>(ceil_div(nb, 8)), static_cast<unsigned>(B * H));
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   score_meanpool_kernel<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, (int)D, scale);
@@ -440,6 +442,7 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
   const size_t smem = 8 * 2 * nk_pad * sizeof(float);
   if (smem > 48 * 1024)
     BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StageTimer timer(2, stream);
   select_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
       scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
       cfg->force_last, idx, cnt, mask_opt, kcut_opt);
