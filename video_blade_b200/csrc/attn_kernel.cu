@@ -37,6 +37,8 @@ constexpr int kBlockN = 128;
 constexpr int kThreads = 384;
 constexpr int kSoftmaxThreads = 128;
 constexpr float kRescaleThresh = 8.0f;  // log2 units
+constexpr int kRegsSoftmax = 224;      // setmaxnreg split: 8 softmax warps x 224 + 4 other warps x 56 = 64512
+constexpr int kRegsOther = 56;
 constexpr int kMaxListSmem = 256;       // per-stream block ids cached in smem by the producer
 constexpr float kLn2 = 0.69314718055994530942f;
 
@@ -125,7 +127,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&mz->q_full[t], 1);
       mbar_init(&mz->q_empty[t], 1);
       mbar_init(&mz->s_full[t], 1);
-      mbar_init(&mz->p_full[t], kSoftmaxThreads);
+      mbar_init(&mz->p_full[t], kSoftmaxThreads / 32);  // one arrival per softmax warp
       mbar_init(&mz->o_full[t], 1);
     }
     for (int s = 0; s < kStages; ++s) {
@@ -151,9 +153,12 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int npt = p.n_pool_tiles;
 
+  // Register split (setmaxnreg) lives INSIDE each role branch: ptxas applies the lowest bound it sees to all
+  // code after a control-flow merge.
   if (warp == 8) {
-    // ============================== TMA producer ==============================
-    uint32_t kv_n = 0;
+    // ============================== TMA producer (warp-uniform; one elected lane issues) ==============
+    setmaxnreg_dec<kRegsOther>();
+    uint32_t slot = 0, ph = 0;  // ring position / phase of the NEXT load
     uint32_t q_it[2] = {0, 0};
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
@@ -168,86 +173,91 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ns[t] = valid ? __ldg(p.cnt + row) : 0;
         nt[t] = valid ? npt + ns[t] : 0;
         lists[t] = p.idx + row * p.idx_stride;
-        // cooperative, coalesced fetch of the block-id list into smem
-        for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32) mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j));
+        // cooperative, coalesced fetch of the block-id list into smem (private to this warp)
+        for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32)
+          mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j));
       }
       __syncwarp();
-      if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (nt[t] == 0) continue;
-          mbar_wait(&mz->q_empty[t], (q_it[t] & 1) ^ 1);
+      for (int t = 0; t < 2; ++t) {
+        if (nt[t] == 0) continue;
+        mbar_wait(&mz->q_empty[t], (q_it[t] & 1) ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&mz->q_full[t], kTileBytes);
 #pragma unroll
           for (int dh = 0; dh < kSub; ++dh)
             tma_load_4d(sQ + t * kTileBytes + dh * (kBlockM * 128), &tmQ, &mz->q_full[t], dh * 64,
                         (2 * pair + t) * kBlockM, h, b, kEvictFirst);
-          ++q_it[t];
         }
-        auto load_tile = [&](int t, int j, bool is_v) {
-          const uint32_t slot = kv_n % kStages;
-          mbar_wait(&mz->kv_empty[slot], ((kv_n / kStages) & 1) ^ 1);
+        __syncwarp();
+        ++q_it[t];
+      }
+      auto load_tile = [&](int t, int j, bool is_v) {
+        mbar_wait(&mz->kv_empty[slot], ph ^ 1);
+        const CUtensorMap* map;
+        int row;
+        if (j < npt) {
+          map = is_v ? &tmVp : &tmKp;
+          row = j * kBlockN;
+        } else {
+          const int jj = j - npt;
+          const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : __ldg(lists[t] + jj);
+          map = is_v ? &tmV : &tmK;
+          row = kb * kBlockN;
+        }
+        if (elect_one()) {
           mbar_arrive_expect_tx(&mz->kv_full[slot], kTileBytes);
-          const CUtensorMap* map;
-          int row;
-          if (j < npt) {
-            map = is_v ? &tmVp : &tmKp;
-            row = j * kBlockN;
-          } else {
-            const int jj = j - npt;
-            const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : __ldg(lists[t] + jj);
-            map = is_v ? &tmV : &tmK;
-            row = kb * kBlockN;
-          }
 #pragma unroll
           for (int dh = 0; dh < kSub; ++dh)
             tma_load_4d(sKV + slot * kTileBytes + dh * (kBlockN * 128), map, &mz->kv_full[slot], dh * 64, row, h, b,
                         kEvictLast);
-          ++kv_n;
-        };
-        const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
-        if (nt[0]) load_tile(0, 0, false);
-        if (nt[1]) load_tile(1, 0, false);
-        for (int j = 0; j < nmax; ++j) {
+        }
+        __syncwarp();
+        if (++slot == kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
+      };
+      const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
+      if (nt[0]) load_tile(0, 0, false);
+      if (nt[1]) load_tile(1, 0, false);
+      for (int j = 0; j < nmax; ++j) {
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (j < nt[t]) {
-              load_tile(t, j, true);
-              if (j + 1 < nt[t]) load_tile(t, j + 1, false);
-            }
+        for (int t = 0; t < 2; ++t) {
+          if (j < nt[t]) {
+            load_tile(t, j, true);
+            if (j + 1 < nt[t]) load_tile(t, j + 1, false);
           }
         }
       }
-      __syncwarp();
     }
   } else if (warp == 9) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kBlockM, kBlockN, IS_BF16, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kBlockM, D, IS_BF16, false, true);
-      uint32_t kv_c = 0;
-      uint32_t g[2] = {0, 0};
-      uint32_t q_it[2] = {0, 0};
-      const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
-        int nt[2];
+    // ============================== MMA issuer (warp-uniform; one elected lane issues) ==============
+    setmaxnreg_dec<kRegsOther>();
+    constexpr uint32_t idesc_qk = make_idesc_f16(kBlockM, kBlockN, IS_BF16, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_f16(kBlockM, D, IS_BF16, false, true);
+    uint32_t slot = 0, ph = 0;  // ring position / phase of the NEXT tile to consume
+    uint32_t g[2] = {0, 0};
+    uint32_t q_it[2] = {0, 0};
+    const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+      int nt[2];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int qb = 2 * pair + t;
-          nt[t] = qb < p.nq ? npt + __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb) : 0;
-        }
+      for (int t = 0; t < 2; ++t) {
+        const int qb = 2 * pair + t;
+        nt[t] = qb < p.nq ? npt + __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb) : 0;
+      }
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (nt[t] == 0) continue;
-          mbar_wait(&mz->q_full[t], q_it[t] & 1);
-          ++q_it[t];
-        }
+      for (int t = 0; t < 2; ++t) {
+        if (nt[t] == 0) continue;
+        mbar_wait(&mz->q_full[t], q_it[t] & 1);
+        ++q_it[t];
+      }
+      auto issue_qk = [&](int t, bool last) {
+        mbar_wait(&mz->kv_full[slot], ph);
         tc_fence_after();
-        auto issue_qk = [&](int t, bool last) {
-          const uint32_t slot = kv_c % kStages;
-          mbar_wait(&mz->kv_full[slot], (kv_c / kStages) & 1);
-          tc_fence_after();
+        if (elect_one()) {
           const uint64_t adesc = make_smem_desc(sQ_addr + t * kTileBytes, 16, 1024, 2);
           const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, 16, 1024, 2);
           const uint32_t tS = tmem_base + t * kBlockN;
@@ -257,14 +267,19 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_commit(&mz->kv_empty[slot]);
           tc_commit(&mz->s_full[t]);
           if (last) tc_commit(&mz->q_empty[t]);
-          ++kv_c;
-        };
-        auto issue_pv = [&](int t, bool fresh) {
-          mbar_wait(&mz->p_full[t], g[t] & 1);
-          const uint32_t slot = kv_c % kStages;
-          mbar_wait(&mz->kv_full[slot], (kv_c / kStages) & 1);
-          tc_fence_after();
-          // V tile: [kv 128][D] as D/64 sub-tiles [128][64], MN-major for B: LBO = sub-tile stride, SBO = 8 kv rows
+        }
+        __syncwarp();
+        if (++slot == kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
+      };
+      auto issue_pv = [&](int t, bool fresh) {
+        mbar_wait(&mz->p_full[t], g[t] & 1);
+        mbar_wait(&mz->kv_full[slot], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          // V tile [kv 128][D] as D/64 sub-tiles [128][64]; MN-major B: LBO = sub-tile stride, SBO = 8 kv rows
           const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, kBlockN * 128, 1024, 2);
           const uint32_t tP = tmem_base + t * kBlockN;
           const uint32_t tO = tmem_base + 2 * kBlockN + t * D;
@@ -273,26 +288,30 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_ts(tO, tP + k * 8, bdesc + k * (16 * 128 / 16), idesc_pv, (!fresh) || k > 0);
           tc_commit(&mz->kv_empty[slot]);
           tc_commit(&mz->o_full[t]);
-          ++kv_c;
-          ++g[t];
-        };
-        const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
-        if (nt[0]) issue_qk(0, nt[0] == 1);
-        if (nt[1]) issue_qk(1, nt[1] == 1);
-        for (int j = 0; j < nmax; ++j) {
+        }
+        __syncwarp();
+        if (++slot == kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
+        ++g[t];
+      };
+      const int nmax = nt[0] > nt[1] ? nt[0] : nt[1];
+      if (nt[0]) issue_qk(0, nt[0] == 1);
+      if (nt[1]) issue_qk(1, nt[1] == 1);
+      for (int j = 0; j < nmax; ++j) {
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (j < nt[t]) {
-              issue_pv(t, j == 0 || j == npt);
-              if (j + 1 < nt[t]) issue_qk(t, j + 2 == nt[t]);
-            }
+        for (int t = 0; t < 2; ++t) {
+          if (j < nt[t]) {
+            issue_pv(t, j == 0 || j == npt);
+            if (j + 1 < nt[t]) issue_qk(t, j + 2 == nt[t]);
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp < 8) {
     // ============================== softmax warpgroups ==============================
+    setmaxnreg_inc<kRegsSoftmax>();
     const int t = warp >> 2;
     const int wq = warp & 3;
     const int row_in_tile = wq * 32 + lane;
@@ -328,22 +347,20 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
           tmem_wait_ld();
           const int valid = (j == ntile - 1) ? tail_valid : kBlockN;
-          float mx = -INFINITY;
+          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max chains
           if (valid < kBlockN) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
+              for (int i = 0; i < 32; ++i)
                 if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
-                mx = fmaxf(mx, __uint_as_float(s[c][i]));
-              }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
           }
-          mx *= sl2;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              mxc[c] = fmaxf(mxc[c], fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sl2;
           if (j == 0) {
             m = mx;
           } else {
@@ -369,7 +386,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           const float neg_m = -m;
-          float lsum = 0.f;
+          float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent sum chains
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[16];
@@ -377,15 +394,16 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < 16; ++i) {
               const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), sl2, neg_m));
               const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, neg_m));
-              lsum += p0 + p1;
+              ls[i & 3] += p0 + p1;
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }
             tmem_st16(tS + c * 16, pk);
           }
-          l += lsum;
+          l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&mz->p_full[t]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mz->p_full[t]);
         }
         // ---- phase finalisation: the last PV of this phase has to retire first
         mbar_wait(&mz->o_full[t], (g - 1) & 1);
@@ -474,6 +492,8 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
       }
     }
+  } else {
+    setmaxnreg_dec<kRegsOther>();  // warps 10, 11: idle (warp 11 owns the TMEM allocation)
   }
 
   tc_fence_before();

@@ -12,7 +12,7 @@ namespace blade {
 #ifndef BLADE_SPIN_LIMIT
 // Bounded spins: a protocol bug traps instead of hanging the GPU box.  ~2^28 polls of >=20ns each
 // is seconds -- far beyond any legitimate wait inside one attention launch.
-#define BLADE_SPIN_LIMIT (1u << 28)
+#define BLADE_SPIN_LIMIT 0x4000000
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -61,16 +61,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Waits for completion of the phase with the given parity.
+// Waits for completion of the phase with the given parity.  The spin lives inside one asm block so the
+// compiler sees straight-line, warp-uniform code (a C++ loop on the per-lane predicate makes every caller
+// "divergent" and wraps each following tcgen05/TMA issue in ELECT/R2UR loops).  Bounded: a protocol bug traps
+// instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > BLADE_SPIN_LIMIT) {
-      printf("blade: mbarrier timeout blk %d thr %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 c;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "BLADE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra BLADE_DONE;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, %2;\n\t"
+      "@p bra BLADE_WAIT;\n\t"
+      "trap;\n\t"
+      "BLADE_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "n"(BLADE_SPIN_LIMIT)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
