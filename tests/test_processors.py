@@ -1,0 +1,108 @@
+"""Processor / installer surface (modify_wan.py MW:75-168, modify_cogvideo.py MC:11-91).
+CPU part: installers wire the objects exactly like the reference.  GPU part: a processor call through the
+CUDA ASA layer equals the same processor with the oracle as `inner_attention`."""
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import asa_oracle as O
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, heads, qk_norm):
+        super().__init__()
+        from video_blade_b200.modify_wan import Attention
+        self.attn1 = Attention(dim, heads, qk_norm=qk_norm)
+        self.attn1.set_processor("stock")
+
+
+def test_installers_wire_like_the_reference():
+    from video_blade_b200 import modify_cogvideo as MC, modify_wan as MW
+    model = types.SimpleNamespace(blocks=nn.ModuleList([_Block(64, 2, "rms_norm_across_heads") for _ in range(3)]))
+    inner = MW.set_adaptive_block_sparse_attn_wanx(model, verbose=True)
+    for b in model.blocks:
+        assert b.attn1.inner_attention is inner                  # one shared module (MW:154-158)
+        assert isinstance(b.attn1.get_processor(), MW.WanAttnProcessor2_0)
+        assert b.attn1.origin_processor == "stock" and b.attn1.verbose is True
+    model = types.SimpleNamespace(transformer_blocks=nn.ModuleList([_Block(64, 2, "layer_norm") for _ in range(2)]))
+    inner = MC.set_block_sparse_attn_cogvideox(model)
+    for i, b in enumerate(model.transformer_blocks):
+        assert b.attn1.inner_attention is inner
+        assert isinstance(b.attn1.get_processor(), MC.SageAttnCogVideoXAttnProcessor)
+        assert b.attn1.get_processor().idx == i and b.attn1.origin_processor == "stock"
+
+
+def test_wan_rope_fp32_matches_reference_fp64():
+    from video_blade_b200.modify_wan import apply_rotary_emb
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 2, 50, 16, generator=g).bfloat16()
+    ang = torch.rand(1, 1, 50, 8, generator=g, dtype=torch.float64) * 6.28
+    freqs = torch.polar(torch.ones_like(ang), ang)
+    ref = O.apply_rotary_emb_wan(x, freqs)
+    got = apply_rotary_emb(x, freqs.to(torch.complex64))
+    assert (got.float() - ref.float()).abs().max() <= 2 ** -6      # <= 1 bf16 ulp at |x| < 4
+
+
+@pytest.mark.gpu
+def test_wan_processor_end_to_end():
+    from video_blade_b200 import modify_wan as MW, wanx_blocksparseattn as W
+    grid = (26, 15, 4)
+    S, H, D = grid[0] * grid[1] * grid[2], 2, 128
+    W.width, W.height, W.depth, W.max_retain_ratio = *grid, 0.4
+    try:
+        torch.manual_seed(0)
+        model = types.SimpleNamespace(blocks=nn.ModuleList([_Block(H * D, H, "rms_norm_across_heads")]))
+        model.blocks.to("cuda", torch.bfloat16)
+        inner = MW.set_adaptive_block_sparse_attn_wanx(model)
+        inner.print_every = 0
+        attn = model.blocks[0].attn1
+        x = torch.randn(1, S, H * D, device="cuda", dtype=torch.bfloat16)
+        ang = torch.rand(1, 1, S, D // 2, device="cuda") * 6.28
+        freqs = torch.polar(torch.ones_like(ang), ang)
+        out = attn(x, rotary_emb=freqs)
+        assert out.shape == x.shape and out.dtype == x.dtype and torch.isfinite(out.float()).all()
+
+        # same processor, oracle as inner attention (fed the kernel's own fp32 scores)
+        captured = {}
+
+        class OracleInner:
+            def __call__(self, q, k, v):
+                eng = W._engine()
+                _, dbg = eng.forward(q, k, v, return_debug=True)
+                cfg = O.ASAConfig.wan(width=grid[0], height=grid[1], depth=grid[2], max_retain_ratio=0.4)
+                res = O.asa_forward(q.cpu(), k.cpu(), v.cpu(), cfg, scores=dbg["scores"].cpu())
+                captured["mask_equal"] = torch.equal(res.mask, dbg["mask"].cpu())
+                return res.out.to(q.device)
+        attn.inner_attention = OracleInner()
+        ref = attn(x, rotary_emb=freqs)
+        assert captured["mask_equal"]
+        d = out.float() - ref.float()
+        assert float(d.norm() / ref.float().norm()) <= 1e-2 and float(d.abs().max()) <= 2e-2
+    finally:
+        W.width, W.height, W.depth, W.max_retain_ratio = 52, 30, 21, 0.17
+
+
+@pytest.mark.gpu
+def test_cog_processor_end_to_end():
+    from video_blade_b200 import cogvideo_blocksparseattn as C, modify_cogvideo as MC
+    grid, T = (15, 10, 6), 40
+    Sv, H, D = grid[0] * grid[1] * grid[2], 3, 64
+    C.width, C.height, C.depth, C.text_length, C.max_retain_ratio = *grid, T, 0.3
+    try:
+        torch.manual_seed(1)
+        model = types.SimpleNamespace(transformer_blocks=nn.ModuleList([_Block(H * D, H, "layer_norm")]))
+        model.transformer_blocks.to("cuda", torch.bfloat16)
+        inner = MC.set_block_sparse_attn_cogvideox(model)
+        inner.print_every = 0
+        attn = model.transformer_blocks[0].attn1
+        x = torch.randn(1, Sv, H * D, device="cuda", dtype=torch.bfloat16)
+        txt = torch.randn(1, T, H * D, device="cuda", dtype=torch.bfloat16)
+        ang = torch.rand(Sv, D // 2, device="cuda") * 6.28
+        cos, sin = ang.cos().repeat_interleave(2, -1), ang.sin().repeat_interleave(2, -1)
+        hs, ehs = attn(x, encoder_hidden_states=txt, image_rotary_emb=(cos, sin))
+        assert hs.shape == x.shape and ehs.shape == txt.shape
+        assert torch.isfinite(hs.float()).all() and torch.isfinite(ehs.float()).all()
+    finally:
+        C.width, C.height, C.depth, C.text_length, C.max_retain_ratio = 45, 30, 13, 226, 0.1

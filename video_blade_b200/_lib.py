@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libblade_asa.so")
+LIB_PATH = os.environ.get("BLADE_ASA_LIB") or os.path.join(HERE, "lib", "libblade_asa.so")
 
 BF16, F16, F32, I32, U8 = 0, 1, 2, 3, 4
 

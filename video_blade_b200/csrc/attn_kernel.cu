@@ -39,6 +39,10 @@ constexpr int kSoftmaxThreads = 128;
 constexpr float kRescaleThresh = 8.0f;  // log2 units
 constexpr int kRegsSoftmax = 224;      // setmaxnreg split: 8 softmax warps x 224 + 4 other warps x 56 = 64512
 constexpr int kRegsOther = 56;
+#ifndef BLADE_POLY_MASK
+#define BLADE_POLY_MASK 0x00  // bit i set: element i of every 8 uses ex2_poly.  Measured on B200 (profiles/README.md): 0x00 1.22 ms, 0x22 1.25, 0x2A 1.32, 0xAA 1.37 -> off
+#endif
+constexpr unsigned kPolyMask = BLADE_POLY_MASK;
 constexpr int kMaxListSmem = 256;       // per-stream block ids cached in smem by the producer
 constexpr float kLn2 = 0.69314718055994530942f;
 
@@ -392,8 +396,12 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), sl2, neg_m));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, neg_m));
+              // exp2 is split between the MUFU pipe and a polynomial on the FMA pipe (kPolyMask picks which
+              // of every 8 elements take the polynomial): MUFU alone (16/clk/SM) costs as much as the MMAs.
+              const float x0 = fmaf(__uint_as_float(s[c][2 * i]), sl2, neg_m);
+              const float x1 = fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, neg_m);
+              const float p0 = ((kPolyMask >> ((2 * i) & 7)) & 1) ? ex2_poly(x0) : ex2_approx(x0);
+              const float p1 = ((kPolyMask >> ((2 * i + 1) & 7)) & 1) ? ex2_poly(x1) : ex2_approx(x1);
               ls[i & 3] += p0 + p1;
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }

@@ -198,36 +198,57 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// scores: grid (ceil(nb/8), B*H), 256 threads, one warp per score row.  dynamic smem: 8*(D + nb) floats
+// scores: grid (ceil(nb/8), B*H), 256 threads, one warp per score row; the head's K means stream through
+// shared memory in chunks of 32 key blocks (coalesced float4 loads, rows padded to D+4 floats so that the
+// per-lane float4 reads are bank-conflict free).  dynamic smem: (8*(D+nb) + 32*(D+4)) floats
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
                                                              float* __restrict__ scores, int nb, int D, float scale) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sq = sm + warp * (D + nb);
-  float* srow = sq + D;
+  const int DP = D + 4;
+  float* sq = sm + warp * D;                 // [8][D]
+  float* srow = sm + 8 * D + warp * nb;      // [8][nb]
+  float* sk = sm + 8 * (D + nb);             // [32][DP]
   const int i = blockIdx.x * 8 + warp;
+  const bool active = i < nb;
   const int64_t bh = blockIdx.y;
-  if (i >= nb) return;
-  const float* qrow = qm + (bh * nb + i) * D;
-  for (int d = lane; d < D; d += 32) sq[d] = qrow[d];
-  __syncwarp();
-  const float* kb = km + bh * nb * D;
-  float mx = -INFINITY;
-  for (int j = lane; j < nb; j += 32) {
-    const float4* kr = reinterpret_cast<const float4*>(kb + static_cast<int64_t>(j) * D);
-    float dot = 0.f;
-    for (int d4 = 0; d4 < D / 4; ++d4) {
-      const float4 kv = __ldg(kr + d4);
-      dot = fmaf(sq[4 * d4 + 0], kv.x, dot);
-      dot = fmaf(sq[4 * d4 + 1], kv.y, dot);
-      dot = fmaf(sq[4 * d4 + 2], kv.z, dot);
-      dot = fmaf(sq[4 * d4 + 3], kv.w, dot);
-    }
-    dot *= scale;
-    srow[j] = dot;
-    mx = fmaxf(mx, dot);
+  if (active) {
+    const float* qrow = qm + (bh * nb + i) * D;
+    for (int d = lane; d < D; d += 32) sq[d] = qrow[d];
   }
+  const float* kb = km + bh * nb * D;
+  const int d4n = D / 4;
+  float mx = -INFINITY;
+  for (int j0 = 0; j0 < nb; j0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * d4n; e += 256) {
+      const int r = e / d4n, c = e % d4n;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < nb) v = __ldg(reinterpret_cast<const float4*>(kb + static_cast<int64_t>(j0 + r) * D) + c);
+      *reinterpret_cast<float4*>(sk + r * DP + 4 * c) = v;
+    }
+    __syncthreads();
+    if (active && j0 + lane < nb) {
+      const float4* kr = reinterpret_cast<const float4*>(sk + lane * DP);
+      const float4* qr = reinterpret_cast<const float4*>(sq);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < d4n; ++c) {
+        const float4 kv = kr[c];
+        const float4 qv = qr[c];
+        d0 = fmaf(qv.x, kv.x, d0);
+        d1 = fmaf(qv.y, kv.y, d1);
+        d2 = fmaf(qv.z, kv.z, d2);
+        d3 = fmaf(qv.w, kv.w, d3);
+      }
+      const float dot = ((d0 + d1) + (d2 + d3)) * scale;
+      srow[j0 + lane] = dot;
+      mx = fmaxf(mx, dot);
+    }
+  }
+  if (!active) return;
+  __syncwarp();
 #pragma unroll
   for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   float sum = 0.f;
@@ -244,14 +265,16 @@ __global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// select: grid ceil(rows/8), 256 threads, one warp per score row.  dynamic smem: 8 * 2 * nk_pad floats
+// select: grid ceil(rows/8), 256 threads, one warp per score row.  dynamic smem: 8 * 2 * nk_pad floats.
+// NSLOT = ceil(nk/32) elements per lane, ranks kept in registers (NSLOT == 0: generic two-pass fallback).
 // ------------------------------------------------------------------------------------------------
+template <int NSLOT>
 __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int64_t total_rows, int nq, int nk,
                                                      int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
                                                      const int32_t* __restrict__ hi_bh, float thr, int force_last,
                                                      int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
                                                      uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_pad = (nk + 31) & ~31;
   float* vals = sm + warp * 2 * nk_pad;
@@ -264,23 +287,53 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   for (int j = lane; j < nk_pad; j += 32) vals[j] = j < nk ? src[j] : -INFINITY;
   __syncwarp();
 
-  // rank of element j under (value desc, index asc): #{i : v_i > v_j or (v_i == v_j and i < j)}
-  const int nslot = nk_pad / 32;
-  for (int s = 0; s < nslot; ++s) {
-    const int j = s * 32 + lane;
-    const float vj = vals[j];
-    int rank = 0;
-    for (int i = 0; i < nk; ++i) {
-      const float vi = vals[i];  // warp-uniform address: smem broadcast
-      rank += (vi > vj) || (vi == vj && i < j);
+  // rank of element j under (value desc, index asc): #{i : v_i > v_j or (v_i == v_j and i < j)}.
+  // Padding entries are -inf at indices >= nk, so they never outrank a real element.
+  constexpr int NS = NSLOT > 0 ? NSLOT : 1;
+  int rank[NS];
+  auto rank_of = [&](int j, float vj) {
+    int r = 0;
+    for (int i4 = 0; i4 < nk_pad; i4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(vals + i4);  // warp-uniform address: broadcast
+      r += (v.x > vj) || (v.x == vj && i4 + 0 < j);
+      r += (v.y > vj) || (v.y == vj && i4 + 1 < j);
+      r += (v.z > vj) || (v.z == vj && i4 + 2 < j);
+      r += (v.w > vj) || (v.w == vj && i4 + 3 < j);
     }
-    if (j < nk) sorted[rank] = vj;
-    // stash the rank where the value was (vals no longer needed for this j after the loop? other lanes
-    // still read vals[j] in later slots, so ranks go to registers via a second pass below)
+    return r;
+  };
+  if (NSLOT > 0) {
+    float vj[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      vj[s] = vals[s * 32 + lane];
+      rank[s] = 0;
+    }
+    for (int i4 = 0; i4 < nk_pad; i4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(vals + i4);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int j = s * 32 + lane;
+        rank[s] += (v.x > vj[s]) || (v.x == vj[s] && i4 + 0 < j);
+        rank[s] += (v.y > vj[s]) || (v.y == vj[s] && i4 + 1 < j);
+        rank[s] += (v.z > vj[s]) || (v.z == vj[s] && i4 + 2 < j);
+        rank[s] += (v.w > vj[s]) || (v.w == vj[s] && i4 + 3 < j);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s * 32 + lane < nk) sorted[rank[s]] = vj[s];
+  } else {
+    for (int j = lane; j < nk; j += 32) {
+      const float vj = vals[j];
+      sorted[rank_of(j, vj)] = vj;
+    }
   }
   __syncwarp();
 
   // fp64 sequential prefix sums, each prefix rounded to fp32 (torch.cumsum on CPU); find the cut.
+  const int lo = lo_bh ? lo_bh[bh] : lo_s;
+  const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kfirst = nk;
   if (lane == 0) {
     double acc = 0.0;
@@ -288,7 +341,8 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
     const float total = static_cast<float>(acc);
     const float th = __fmul_rn(thr, total);
     acc = 0.0;
-    for (int i = 0; i < nk; ++i) {
+    const int lim = hi < nk ? hi : nk;  // beyond `hi` the clamp decides: no need to look further
+    for (int i = 0; i < lim; ++i) {
       acc += static_cast<double>(sorted[i]);
       if (static_cast<float>(acc) >= th) {
         kfirst = i;
@@ -297,8 +351,6 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
     }
   }
   kfirst = __shfl_sync(0xffffffffu, kfirst, 0);
-  const int lo = lo_bh ? lo_bh[bh] : lo_s;
-  const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kc = kfirst < lo ? lo : kfirst;
   kc = kc > hi ? hi : kc;
   if (kcut && lane == 0) kcut[row] = kc;
@@ -307,15 +359,18 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   int32_t* irow = idx + row * nk;
   uint8_t* mrow = mask ? mask + row * nk : nullptr;
   int base = 0;
+  const int nslot = nk_pad / 32;
   for (int s = 0; s < nslot; ++s) {
     const int j = s * 32 + lane;
-    const float vj = vals[j];
-    int rank = 0;
-    for (int i = 0; i < nk; ++i) {
-      const float vi = vals[i];
-      rank += (vi > vj) || (vi == vj && i < j);
+    int rk;
+    if (NSLOT > 0) {
+      rk = 0;
+#pragma unroll
+      for (int u = 0; u < NS; ++u) rk = (u == s) ? rank[u] : rk;
+    } else {
+      rk = rank_of(j, vals[j]);
     }
-    bool sel = j < nk && (rank < kc || full_row || (force_last > 0 && j >= nk - force_last));
+    const bool sel = j < nk && (rk < kc || full_row || (force_last > 0 && j >= nk - force_last));
     const unsigned bal = __ballot_sync(0xffffffffu, sel);
     if (sel) irow[base + __popc(bal & ((1u << lane) - 1u))] = j;
     if (mrow && j < nk) mrow[j] = sel ? 1 : 0;
@@ -418,7 +473,7 @@ extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mea
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BLADE_REQUIRE(q_mean && k_mean && scores, BLADE_ERR_ARG, "null pointer");
   BLADE_REQUIRE(D % 4 == 0 && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
-  const size_t smem = 8 * (D + nb) * sizeof(float);
+  const size_t smem = (8 * (D + nb) + 32 * (D + 4)) * sizeof(float);
   BLADE_REQUIRE(smem <= 200 * 1024, BLADE_ERR_SHAPE, "nb too large for score kernel");
   if (smem > 48 * 1024)
     BLADE_CUDA_OK(cudaFuncSetAttribute(score_meanpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -440,12 +495,28 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
   const int64_t rows = B * H * nq;
   const int nk_pad = static_cast<int>((nk + 31) & ~31);
   const size_t smem = 8 * 2 * nk_pad * sizeof(float);
-  if (smem > 48 * 1024)
-    BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StageTimer timer(2, stream);
-  select_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
-      scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
-      cfg->force_last, idx, cnt, mask_opt, kcut_opt);
+  const int nslot = nk_pad / 32;
+#define LAUNCH_SELECT(NS)                                                                                          \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    select_kernel<NS><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(                            \
+        scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,     \
+        cfg->force_last, idx, cnt, mask_opt, kcut_opt);                                                            \
+  } while (0)
+  switch (nslot) {
+    case 1: LAUNCH_SELECT(1); break;
+    case 2: LAUNCH_SELECT(2); break;
+    case 3: LAUNCH_SELECT(3); break;
+    case 4: LAUNCH_SELECT(4); break;
+    case 5: LAUNCH_SELECT(5); break;
+    case 6: LAUNCH_SELECT(6); break;
+    case 7: LAUNCH_SELECT(7); break;
+    case 8: LAUNCH_SELECT(8); break;
+    default: LAUNCH_SELECT(0); break;
+  }
+#undef LAUNCH_SELECT
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
 }

@@ -221,6 +221,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite range reduction with the 1.5*2^23 magic-number trick and a
+// degree-3 polynomial (max relative error 7.7e-5, far below the bf16 rounding P receives).  Valid for
+// x <= ~100; x is clamped at -125 so the result stays a normal float (exp2(-inf) -> 2^-125 ~ 2e-38).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;   // integer part of x now sits in the low mantissa bits of t
+  const float fl = t - 12582912.0f;  // round-to-nearest(x)
+  const float f = x - fl;            // [-0.5, 0.5]
+  float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+  p = fmaf(p, f, 0.6932762265205383f);
+  p = fmaf(p, f, 0.9999289512634277f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 // pack two fp32 into bf16x2: lo -> bits [0,16), hi -> bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

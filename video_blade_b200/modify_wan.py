@@ -1,0 +1,134 @@
+"""Drop-in mirror of the reference's wanx/train/modify_wan.py (MW): the attention processor and installer for
+diffusers' WanTransformer3DModel.  Same names, same call signature, same `attn.inner_attention(q,k,v)`
+contract (MW:75-168); the inner attention is the B200 ASA engine.
+
+`Attention` below is a duck-typed stand-in for diffusers' attention block (to_q/to_k/to_v, norm_q/norm_k, heads,
+to_out, add_k_proj, set_processor/get_processor) so the path runs where diffusers is not installed; with
+diffusers present the real `block.attn1` objects are used unchanged.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .wanx_blocksparseattn import AdaptiveBlockSparseAttnTrain
+
+
+def apply_rotary_emb(hidden_states: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
+    """MW:110-113: complex multiply of interleaved pairs.  The reference upcasts to float64; fp32 is within
+    bf16 rounding of it (tests/test_processors.py) and keeps the op off the fp64 pipe."""
+    dt = torch.float64 if freqs.dtype == torch.complex128 and not hidden_states.is_cuda else torch.float32
+    x = torch.view_as_complex(hidden_states.to(dt).unflatten(3, (-1, 2)))
+    f = freqs.to(torch.complex64 if dt == torch.float32 else torch.complex128)
+    return torch.view_as_real(x * f).flatten(3, 4).type_as(hidden_states)
+
+
+class WanAttnProcessor2_0:
+    """MW:75-148."""
+
+    def __init__(self):
+        pass
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        encoder_hidden_states_img = None
+        if getattr(attn, "add_k_proj", None) is not None:                     # I2V branch, MW:88-91
+            encoder_hidden_states_img = encoder_hidden_states[:, :257]
+            encoder_hidden_states = encoder_hidden_states[:, 257:]
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+
+        query = attn.to_q(hidden_states)                                       # MW:95-97
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        if attn.norm_q is not None:                                            # MW:99-102
+            query = attn.norm_q(query)
+        if attn.norm_k is not None:
+            key = attn.norm_k(key)
+        query = query.unflatten(2, (attn.heads, -1)).transpose(1, 2)           # MW:104-106: strided views
+        key = key.unflatten(2, (attn.heads, -1)).transpose(1, 2)
+        value = value.unflatten(2, (attn.heads, -1)).transpose(1, 2)
+        if rotary_emb is not None:                                             # MW:108-116
+            query = apply_rotary_emb(query, rotary_emb)
+            key = apply_rotary_emb(key, rotary_emb)
+
+        hidden_states_img = None
+        if encoder_hidden_states_img is not None:                              # MW:118-131
+            key_img = attn.norm_added_k(attn.add_k_proj(encoder_hidden_states_img))
+            value_img = attn.add_v_proj(encoder_hidden_states_img)
+            key_img = key_img.unflatten(2, (attn.heads, -1)).transpose(1, 2)
+            value_img = value_img.unflatten(2, (attn.heads, -1)).transpose(1, 2)
+            hidden_states_img = attn.inner_attention(query, key_img, value_img)
+            hidden_states_img = hidden_states_img.transpose(1, 2).flatten(2, 3).type_as(query)
+
+        hidden_states = attn.inner_attention(query, key, value)                # MW:135
+        hidden_states = hidden_states.transpose(1, 2).flatten(2, 3)            # a view: output memory is [B,S,H,D]
+        hidden_states = hidden_states.type_as(query)
+        if hidden_states_img is not None:
+            hidden_states = hidden_states + hidden_states_img
+        hidden_states = attn.to_out[0](hidden_states)                          # MW:146-147
+        hidden_states = attn.to_out[1](hidden_states)
+        return hidden_states
+
+
+def set_adaptive_block_sparse_attn_wanx(model, verbose=False):
+    """MW:150-168: one shared ASA module for every block's self-attention."""
+    inner_attn = AdaptiveBlockSparseAttnTrain()
+    for idx, block in enumerate(model.blocks):
+        block.attn1.verbose = verbose
+        block.attn1.inner_attention = inner_attn
+        origin_processor = block.attn1.get_processor()
+        processor = WanAttnProcessor2_0()
+        block.attn1.set_processor(processor)
+        if not hasattr(block.attn1, "origin_processor"):
+            block.attn1.origin_processor = origin_processor
+    return inner_attn
+
+
+# ------------------------------------------------------------------------------------------------
+class RMSNorm(nn.Module):
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float()
+        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)
+        return (v * self.weight.float()).type_as(x)
+
+
+class Attention(nn.Module):
+    """Minimal stand-in for diffusers.models.attention_processor.Attention (self-attention use only)."""
+
+    def __init__(self, dim: int, heads: int, qk_norm: str = "rms_norm_across_heads", bias: bool = True,
+                 elementwise_affine: bool = True):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, bias=bias)
+        self.to_k = nn.Linear(dim, dim, bias=bias)
+        self.to_v = nn.Linear(dim, dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim, bias=bias), nn.Dropout(0.0)])
+        if qk_norm == "rms_norm_across_heads":          # Wan: RMSNorm over the full inner dim before the head split
+            self.norm_q, self.norm_k = RMSNorm(dim), RMSNorm(dim)
+        elif qk_norm == "layer_norm":                   # CogVideoX: LayerNorm per head
+            hd = dim // heads
+            self.norm_q = nn.LayerNorm(hd, eps=1e-6, elementwise_affine=elementwise_affine)
+            self.norm_k = nn.LayerNorm(hd, eps=1e-6, elementwise_affine=elementwise_affine)
+        else:
+            self.norm_q = self.norm_k = None
+        self.add_k_proj = None
+        self.is_cross_attention = False
+        self.inner_attention = None
+        self._processor = None
+
+    def set_processor(self, processor):
+        self._processor = processor
+
+    def get_processor(self):
+        return self._processor
+
+    def forward(self, hidden_states, **kw):
+        return self._processor(self, hidden_states, **kw)
