@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""End-to-end 8-step clip benchmark (BASELINE.json config 3): random-init Wan2.1-T2V-1.3B-shaped DiT (30 blocks),
+synthetic latents [B,16,21,60,104] + prompt embeddings [B,512,4096], CFG, `generate_new` sampler, ASA installed
+through the reference-facing installer.  1 GPU: CFG as a batch of two.  N GPUs (torchrun): 2 CFG groups x
+Ulysses N/2 (Wan has 12 heads -> N in {2,4,8}).
+
+    python bench_clip.py [--steps 8] [--layers 30] [--reps 2]
+    python -m torch.distributed.run --nproc-per-node N ... bench_clip.py --gpus N
+
+Prints one JSON line: clip seconds (max over ranks, CUDA events), and the attention share."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--layers", type=int, default=30)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--guidance", type=float, default=5.0)
+    ap.add_argument("--dense", action="store_true", help="replace ASA by dense SDPA (context number)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    from video_blade_b200 import wanx_blocksparseattn as W
+    from video_blade_b200.dit import WanLikeDiT, generate_new, make_velocity_fn
+    from video_blade_b200.modify_wan import set_adaptive_block_sparse_attn_wanx
+    from video_blade_b200.ulysses import UlyssesGroup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == a.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = 1 if world == 1 else world // 2
+    group = UlyssesGroup(world, rank, P) if world > 1 else None
+    branch = 0 if world == 1 else rank // P
+
+    torch.manual_seed(0)
+    model = WanLikeDiT(layers=a.layers).to(dev, torch.bfloat16).eval()
+    inner = set_adaptive_block_sparse_attn_wanx(model)
+    inner.print_every = 0
+    model.set_sequence_parallel(group)
+    if a.dense:
+        class Dense(torch.nn.Module):
+            def forward(self, q, k, v):
+                return torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        for blk in model.blocks:
+            blk.attn1.inner_attention = Dense()
+
+    g = torch.Generator(device="cpu").manual_seed(1)
+    noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
+    prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+    negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+    cfg_ranks = None if world == 1 else (branch, 0, P)
+    vel = make_velocity_fn(model, prompt, negative, a.guidance, cfg_ranks)
+
+    def clip():
+        return generate_new(vel, noise, steps=a.steps)
+
+    with torch.no_grad():
+        generate_new(vel, noise, steps=1)                        # warm-up (cuBLAS plans, workspaces, NCCL)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(a.reps):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            out = clip()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 1e3)
+    t = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": "8-step clip seconds (Wan2.1-T2V-1.3B shape, random init, CFG, synthetic inputs)",
+                "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
+                "config": {"workload": "Wan2.1-T2V-1.3B 81x480x832, 30 DiT blocks, 8 steps, CFG batch 2",
+                           "layers": a.layers, "steps": a.steps, "attention": "dense SDPA" if a.dense else "ASA",
+                           "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}"},
+                "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
+                "avg_sparsity": None if a.dense else inner.average_sparsity()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,227 @@
+"""Minimal random-init Wan2.1-T2V-1.3B-shaped DiT + the 8-step distilled sampler, for the end-to-end clip
+benchmark of BASELINE.json config 3 (synthetic latents / prompt embeddings, no checkpoint, no diffusers).
+
+This is benchmark scaffolding around the hot path, not part of it: every token-wise op is stock PyTorch/cuBLAS
+(as it is in the reference, where diffusers provides them); self-attention goes through the reference-facing
+processor + the B200 ASA engine.  Shapes follow diffusers' WanTransformer3DModel for the 1.3B config: 30 blocks,
+dim 1536, 12 heads x 128, FFN 8960, text dim 4096 (512 tokens), 16 latent channels, patch (1,2,2), adaLN
+modulation from a sinusoidal timestep embedding, 3-axis RoPE (44/42/42 split of the head dim).
+
+Sampler of record: `generate_new` of the reference trainer (train_wanx_tdm.py:1402-1443) with flow sigmas
+(shift 3.0, inference.py:49-50): x0 = x_t - sigma*v, eps = x_t + (1-sigma)*v, t <- t - 1000/K,
+x_t <- (1-sigma')*x0 + sigma'*(eta*eps + sqrt(1-eta^2)*N(0,1)).
+
+Sequence parallelism: with a UlyssesGroup every rank keeps S/P tokens for all token-wise ops and the
+processor wraps `inner_attention` with the head/sequence all-to-all.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modify_wan import Attention, RMSNorm, WanAttnProcessor2_0, apply_rotary_emb
+from .ulysses import UlyssesGroup
+
+
+class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
+    """WanAttnProcessor2_0 (MW:75-148) with the Ulysses exchange around `inner_attention`."""
+
+    def __init__(self, group: Optional[UlyssesGroup]):
+        super().__init__()
+        self.group = group
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
+        if self.group is None or self.group.P == 1:
+            return super().__call__(attn, hidden_states, encoder_hidden_states, attention_mask, rotary_emb)
+        B = hidden_states.shape[0]
+        q = attn.norm_q(attn.to_q(hidden_states)).unflatten(2, (attn.heads, -1))      # [B, S/P, H, D]
+        k = attn.norm_k(attn.to_k(hidden_states)).unflatten(2, (attn.heads, -1))
+        v = attn.to_v(hidden_states).unflatten(2, (attn.heads, -1))
+        if rotary_emb is not None:                                                     # local tokens' freqs
+            q = apply_rotary_emb(q.transpose(1, 2), rotary_emb).transpose(1, 2)
+            k = apply_rotary_emb(k.transpose(1, 2), rotary_emb).transpose(1, 2)
+        outs = []
+        for b in range(B):                                                             # exchange is per sequence
+            gq, gk, gv = self.group.scatter_heads(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
+                                                  v[b:b + 1].contiguous())              # [1, S, H/P, D]
+            o = attn.inner_attention(gq.transpose(1, 2), gk.transpose(1, 2), gv.transpose(1, 2))
+            outs.append(self.group.gather_heads(o.transpose(1, 2)))                    # [1, S/P, H, D]
+        o = torch.cat(outs, 0).flatten(2, 3).type_as(hidden_states)
+        return attn.to_out[1](attn.to_out[0](o))
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.heads = heads
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.to_out = nn.Linear(dim, dim)
+        self.norm_q, self.norm_k = RMSNorm(dim), RMSNorm(dim)
+
+    def forward(self, x, ctx):
+        B, S, C = x.shape
+        q = self.norm_q(self.to_q(x)).view(B, S, self.heads, -1).transpose(1, 2)
+        k = self.norm_k(self.to_k(ctx)).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
+        v = self.to_v(ctx).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v)                                    # 512 text keys: not the hot path
+        return self.to_out(o.transpose(1, 2).reshape(B, S, C))
+
+
+class WanBlock(nn.Module):
+    def __init__(self, dim, heads, ffn):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6, elementwise_affine=False)
+        self.attn1 = Attention(dim, heads, qk_norm="rms_norm_across_heads")
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6, elementwise_affine=True)
+        self.attn2 = CrossAttention(dim, heads)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-6, elementwise_affine=False)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn), nn.GELU(approximate="tanh"), nn.Linear(ffn, dim))
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+
+    def forward(self, x, ctx, temb, rotary_emb):
+        sh_msa, sc_msa, g_msa, sh_mlp, sc_mlp, g_mlp = (self.scale_shift_table + temb.float()).chunk(6, dim=1)
+        h = (self.norm1(x.float()) * (1 + sc_msa) + sh_msa).type_as(x)
+        x = (x.float() + self.attn1(h, rotary_emb=rotary_emb).float() * g_msa).type_as(x)
+        x = x + self.attn2(self.norm2(x.float()).type_as(x), ctx)
+        h = (self.norm3(x.float()) * (1 + sc_mlp) + sh_mlp).type_as(x)
+        x = (x.float() + self.ffn(h).float() * g_mlp).type_as(x)
+        return x
+
+
+def rope_freqs(frames, height, width, head_dim, theta=10000.0, device="cpu"):
+    """Complex rotary table [1,1,S,head_dim/2] over the (f,h,w) token grid, raster order (w fastest)."""
+    dh = dw = 2 * (head_dim // 6)
+    dt = head_dim - dh - dw
+
+    def axis(n, d):
+        inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64, device=device) / d))
+        ang = torch.outer(torch.arange(n, dtype=torch.float64, device=device), inv)
+        return torch.polar(torch.ones_like(ang), ang)
+    ft, fh, fw = axis(frames, dt), axis(height, dh), axis(width, dw)
+    f = torch.cat([ft[:, None, None].expand(frames, height, width, -1), fh[None, :, None].expand(frames, height, width, -1),
+                   fw[None, None, :].expand(frames, height, width, -1)], dim=-1)
+    return f.reshape(1, 1, frames * height * width, head_dim // 2).to(torch.complex64)
+
+
+class WanLikeDiT(nn.Module):
+    def __init__(self, dim=1536, heads=12, ffn=8960, layers=30, text_dim=4096, in_ch=16, patch=(1, 2, 2),
+                 freq_dim=256):
+        super().__init__()
+        self.dim, self.heads, self.in_ch, self.patch, self.freq_dim = dim, heads, in_ch, patch, freq_dim
+        pdim = in_ch * patch[0] * patch[1] * patch[2]
+        self.patch_embedding = nn.Linear(pdim, dim)            # == Conv3d(kernel = stride = patch)
+        self.text_embedding = nn.Sequential(nn.Linear(text_dim, dim), nn.GELU(approximate="tanh"), nn.Linear(dim, dim))
+        self.time_embedding = nn.Sequential(nn.Linear(freq_dim, dim), nn.SiLU(), nn.Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.SiLU(), nn.Linear(dim, 6 * dim))
+        self.blocks = nn.ModuleList([WanBlock(dim, heads, ffn) for _ in range(layers)])
+        self.norm_out = nn.LayerNorm(dim, eps=1e-6, elementwise_affine=False)
+        self.proj_out = nn.Linear(dim, pdim)
+        self.head_table = nn.Parameter(torch.randn(1, 2, dim) / dim ** 0.5)
+        self.group: Optional[UlyssesGroup] = None
+        self._rope = {}
+
+    def set_sequence_parallel(self, group: Optional[UlyssesGroup]):
+        self.group = group
+        for blk in self.blocks:
+            blk.attn1.set_processor(UlyssesWanAttnProcessor(group))
+
+    def patchify(self, lat):                                   # [B,C,F,H,W] -> [B,S,C*p]
+        B, C, Fr, H, W = lat.shape
+        pt, ph, pw = self.patch
+        x = lat.view(B, C, Fr // pt, pt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+        return x.reshape(B, (Fr // pt) * (H // ph) * (W // pw), C * pt * ph * pw), (Fr // pt, H // ph, W // pw)
+
+    def unpatchify(self, x, grid, C):
+        B = x.shape[0]
+        f, h, w = grid
+        pt, ph, pw = self.patch
+        x = x.view(B, f, h, w, C, pt, ph, pw).permute(0, 4, 1, 5, 2, 6, 3, 7)
+        return x.reshape(B, C, f * pt, h * ph, w * pw)
+
+    def timestep_embedding(self, t):
+        half = self.freq_dim // 2
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device=t.device, dtype=torch.float32) / half)
+        args = t.float()[:, None] * freqs[None]
+        return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+    def forward(self, hidden_states, timestep, encoder_hidden_states):
+        """hidden_states [B,16,F,H,W] latents; timestep [B]; encoder_hidden_states [B,512,4096] -> velocity."""
+        x, grid = self.patchify(hidden_states)
+        S = x.shape[1]
+        key = (grid, str(x.device))
+        if key not in self._rope:
+            self._rope[key] = rope_freqs(*grid, self.dim // self.heads, device=x.device)
+        rope = self._rope[key]
+        g = self.group
+        if g is not None and g.P > 1:                          # keep my S/P token shard
+            sl = slice(g.rank_in_group * (S // g.P), (g.rank_in_group + 1) * (S // g.P))
+            x, rope = x[:, sl], rope[:, :, sl]
+        x = self.patch_embedding(x)
+        temb = self.time_embedding(self.timestep_embedding(timestep).type_as(x))
+        tproj = self.time_projection(temb).unflatten(1, (6, -1))
+        ctx = self.text_embedding(encoder_hidden_states)
+        for blk in self.blocks:
+            x = blk(x, ctx, tproj, rope)
+        shift, scale = (self.head_table + temb.float().unsqueeze(1)).chunk(2, dim=1)
+        x = (self.norm_out(x.float()) * (1 + scale) + shift).type_as(x)
+        x = self.proj_out(x)
+        if g is not None and g.P > 1:                          # reassemble the sequence for the sampler update
+            import torch.distributed as dist
+            parts = [torch.empty_like(x) for _ in range(g.P)]
+            dist.all_gather(parts, x.contiguous(), group=g.group)
+            x = torch.cat(parts, dim=1)
+        return self.unpatchify(x, grid, self.in_ch)
+
+
+def flow_sigma(t, shift=3.0, total=1000):
+    s = t.float() / total
+    return shift * s / (1 + (shift - 1) * s)
+
+
+def make_velocity_fn(transformer, prompt_embeds, negative_embeds=None, guidance_scale=1.0, cfg_ranks=None):
+    """Guided velocity v(x_t, T).  Single process: CFG as a batch of two.  `cfg_ranks=(my_branch, cond_rank,
+    uncond_rank)`: the two CFG branches live on different rank groups (no traffic until the combine, which is one
+    small all_gather of the velocity)."""
+    use_cfg = negative_embeds is not None and guidance_scale != 1.0
+
+    def fn(x_t, T):
+        if not use_cfg:
+            return transformer(x_t, T, prompt_embeds)
+        if cfg_ranks is None:
+            v2 = transformer(torch.cat([x_t, x_t]), torch.cat([T, T]), torch.cat([prompt_embeds, negative_embeds]))
+            v_c, v_u = v2.chunk(2)
+        else:
+            import torch.distributed as dist
+            branch, cond_rank, uncond_rank = cfg_ranks
+            v = transformer(x_t, T, prompt_embeds if branch == 0 else negative_embeds).contiguous()
+            parts = [torch.empty_like(v) for _ in range(dist.get_world_size())]
+            dist.all_gather(parts, v)
+            v_c, v_u = parts[cond_rank], parts[uncond_rank]
+        return v_u + guidance_scale * (v_c - v_u)
+    return fn
+
+
+@torch.no_grad()
+def generate_new(velocity_fn, noise, steps=8, eta=1.0, flow_shift=3.0, total_steps=1000, generator=None):
+    """K-step distilled sampling, train_wanx_tdm.py:1402-1443, on a guided-velocity callable."""
+    B = noise.shape[0]
+    T = torch.full((B,), total_steps - 1, device=noise.device, dtype=torch.long)
+    x_t = noise
+    latent = noise
+    for _ in range(steps):
+        v = velocity_fn(x_t, T)
+        sigma = flow_sigma(T, flow_shift, total_steps).view(B, 1, 1, 1, 1).to(x_t.dtype)
+        latent = x_t - sigma * v                                  # predicted x0            (TW:1426)
+        pred_eps = x_t + (1 - sigma) * v                          #                         (TW:1431)
+        T = T - total_steps // steps                              #                         (TW:1435)
+        add_eps = eta * pred_eps
+        if eta != 1.0:
+            add_eps = add_eps + ((1 - eta ** 2) ** 0.5) * torch.randn(pred_eps.shape, device=pred_eps.device,
+                                                                       dtype=pred_eps.dtype, generator=generator)
+        s2 = flow_sigma(T.clamp(min=0), flow_shift, total_steps).view(B, 1, 1, 1, 1).to(x_t.dtype)
+        x_t = (1 - s2) * latent + s2 * add_eps                    # add_noise(latent, add_eps, T)  (TW:1437)
+    return latent
