@@ -67,8 +67,8 @@ def test_wan_processor_end_to_end():
         # same processor, oracle as inner attention (fed the kernel's own fp32 scores)
         captured = {}
 
-        class OracleInner:
-            def __call__(self, q, k, v):
+        class OracleInner(nn.Module):
+            def forward(self, q, k, v):
                 eng = W._engine()
                 _, dbg = eng.forward(q, k, v, return_debug=True)
                 cfg = O.ASAConfig.wan(width=grid[0], height=grid[1], depth=grid[2], max_retain_ratio=0.4)

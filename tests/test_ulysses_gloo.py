@@ -51,3 +51,36 @@ def _worker(rank, world, degree, port, S, H, D):
 def test_ulysses_roundtrip_gloo(world, degree):
     port = _free_port()
     mp.spawn(_worker, args=(world, degree, port, 24, 12, 8), nprocs=world, join=True)
+
+
+def _worker_fused(rank, world, degree, port, S, H, D):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from video_blade_b200.ulysses import UlyssesGroup
+        ug = UlyssesGroup(world, rank, degree)
+        gid, pr = rank // degree, rank % degree
+        g = torch.Generator().manual_seed(7 + gid)
+        full = [torch.randn(1, S, H, D, generator=g) for _ in range(3)]
+        sl = slice(pr * (S // degree), (pr + 1) * (S // degree))
+        qv, kv, vv, vrow, keep = ug.scatter_heads_fused(*(x[:, sl].contiguous() for x in full))
+        Hl = H // degree
+        flat = keep.reshape(-1)
+        for view, ref in zip((qv, kv, vv), full):
+            assert view.shape == (1, Hl, S, D) and view.stride(2) == Hl * D and view.stride(1) == D
+            # token s of the head shard is row vrow[s] of the strided view: the address arithmetic the prep kernel
+            # does (base + vrow * stride_s + h * stride_h + d), emulated on the flat receive buffer
+            off = view.storage_offset() + vrow.long()[None, :, None] * view.stride(2) \
+                + torch.arange(Hl)[:, None, None] * view.stride(1) + torch.arange(D)[None, None, :]
+            got = flat[off]                                                 # [Hl, S, D]
+            want = ref[0, :, pr * Hl:(pr + 1) * Hl].transpose(0, 1)
+            assert torch.equal(got, want)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,degree", [(2, 2), (4, 4)])
+def test_ulysses_fused_scatter_layout_gloo(world, degree):
+    port = _free_port()
+    mp.spawn(_worker_fused, args=(world, degree, port, 24, 12, 8), nprocs=world, join=True)

@@ -237,7 +237,8 @@ class AsaEngine:
         return out
 
     # ---- the whole layer ------------------------------------------------------------------
-    def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False):
+    def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
+                virtual_rows: Optional[torch.Tensor] = None):
         """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
         token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
         processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous."""
@@ -248,6 +249,14 @@ class AsaEngine:
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
         src = self.src_row(dev, S)
+        dst = src
+        if virtual_rows is not None:
+            # q/k/v rows live at `virtual_rows[s]` of a packed buffer (Ulysses receive layout): compose the gather
+            # table with it; the output permutation is unchanged.
+            key = ("v", str(dev), S, virtual_rows.data_ptr())
+            if key not in self._src_row:
+                self._src_row[key] = (virtual_rows[src.long()] if src is not None else virtual_rows).contiguous()
+            src = self._src_row[key]
         nbytes = self.lib.blade_asa_workspace_bytes(B, H, S, D, C.byref(cfg))
         ws = self.workspace(dev, nbytes)
         out = torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)
@@ -261,7 +270,7 @@ class AsaEngine:
             scores = scores.contiguous()
             assert scores.dtype == torch.float32 and tuple(scores.shape) == (B, H, nb, nb)
         check(self.lib.blade_asa_forward(
-            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), ptr(src), ptr(src),
+            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), ptr(src), ptr(dst),
             C.byref(cfg), ptr(scores), C.byref(tensor_desc(out)), ptr(sc_out), ptr(mask), ptr(idx), cnt.data_ptr(),
             ws.data_ptr(), ws.numel(), current_stream()))
         if return_debug:

@@ -158,10 +158,12 @@ class AdaptiveBlockSparseAttnTrain(nn.Module):
         self._cnt_den = 0
         self.print_every = 800
 
-    def forward(self, q, k, v):
+    def forward(self, q, k, v, virtual_rows=None):
+        """`virtual_rows` (optional, int32 [S]): q/k/v are strided views into a packed Ulysses receive buffer and
+        token s lives at row virtual_rows[s] (video_blade_b200.ulysses.scatter_heads_fused)."""
         m = sys.modules[__name__]
         eng = _engine(use_rearrange=bool(self.use_rearrange))
-        out, cnt = eng.forward(q, k, v)
+        out, cnt = eng.forward(q, k, v, virtual_rows=virtual_rows)
         # sparsity bookkeeping without the reference's per-layer .item() sync (W:398): accumulate on device
         if self._cnt_acc is None or self._cnt_acc.device != cnt.device:
             self._cnt_acc = torch.zeros((), dtype=torch.float64, device=cnt.device)

@@ -46,9 +46,9 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
             k = apply_rotary_emb(k.transpose(1, 2), rotary_emb).transpose(1, 2)
         outs = []
         for b in range(B):                                                             # exchange is per sequence
-            gq, gk, gv = self.group.scatter_heads(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
-                                                  v[b:b + 1].contiguous())              # [1, S, H/P, D]
-            o = attn.inner_attention(gq.transpose(1, 2), gk.transpose(1, 2), gv.transpose(1, 2))
+            gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
+                                                                     v[b:b + 1].contiguous())   # one all_to_all
+            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow)                    # [1, H/P, S, D]
             outs.append(self.group.gather_heads(o.transpose(1, 2)))                    # [1, S/P, H, D]
         o = torch.cat(outs, 0).flatten(2, 3).type_as(hidden_states)
         return attn.to_out[1](attn.to_out[0](o))
@@ -86,7 +86,7 @@ class WanBlock(nn.Module):
         sh_msa, sc_msa, g_msa, sh_mlp, sc_mlp, g_mlp = (self.scale_shift_table + temb.float()).chunk(6, dim=1)
         h = (self.norm1(x.float()) * (1 + sc_msa) + sh_msa).type_as(x)
         x = (x.float() + self.attn1(h, rotary_emb=rotary_emb).float() * g_msa).type_as(x)
-        x = x + self.attn2(self.norm2(x.float()).type_as(x), ctx)
+        x = x + self.attn2(self.norm2(x), ctx)
         h = (self.norm3(x.float()) * (1 + sc_mlp) + sh_mlp).type_as(x)
         x = (x.float() + self.ffn(h).float() * g_mlp).type_as(x)
         return x
