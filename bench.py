@@ -267,19 +267,51 @@ def run_blade(args):
     dev_ms = sum(per_step)
     stage_ms = [sum(ev[i][s][0].elapsed_time(ev[i][s][1]) for i in range(args.steps)) / args.steps for s in range(4)]
 
-    # ---- e2e: host buffers, H2D + layer + D2H inside the timed region
-    def e2e_step():
-        a = hq.to(dev, non_blocking=True)
-        b = hk.to(dev, non_blocking=True)
-        c = hv.to(dev, non_blocking=True)
-        oo, _ = layer(a, b, c)
-        out_host.copy_(oo, non_blocking=True)
-    for _ in range(min(2, args.warmup)):
-        e2e_step()
+    # ---- e2e: host buffers; every step copies its q,k,v from pinned host memory and reads its output back.
+    # The three stages run on three streams with double-buffered device tensors (step i+1's H2D and step i-1's D2H
+    # overlap step i's kernels), the way a serving loop would drive the C ABI; all copies are inside the timed region.
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    s_main = torch.cuda.current_stream()
+    dbuf = [[torch.empty_like(dq) for _ in range(3)] for _ in range(2)]
+    obuf = [torch.empty_like(out_host) for _ in range(2)]
+    ohost = [torch.empty(dq.shape, dtype=dq.dtype).pin_memory() for _ in range(2)]
+
+    def e2e_run(nsteps):
+        ev_in = [torch.cuda.Event() for _ in range(nsteps)]
+        ev_cmp = [torch.cuda.Event() for _ in range(nsteps)]
+        ev_out = [torch.cuda.Event() for _ in range(nsteps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s_main)
+        s_in.wait_event(e0); s_out.wait_event(e0)
+        for i in range(nsteps):
+            slot = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_cmp[i - 2])                     # slot's previous consumer is done
+                for dst, src in zip(dbuf[slot], (hq, hk, hv)):
+                    dst.copy_(src, non_blocking=True)
+                ev_in[i].record(s_in)
+            s_main.wait_event(ev_in[i])
+            if i >= 2:
+                s_main.wait_event(ev_out[i - 2])                       # output slot drained
+            oo, _ = layer(*dbuf[slot])
+            obuf_i = oo                                                # [1,S,H,D] view of fresh memory
+            ev_cmp[i].record(s_main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[i])
+                ohost[slot].copy_(obuf_i, non_blocking=True)
+                obuf_i.record_stream(s_out)
+                ev_out[i].record(s_out)
+        s_main.wait_stream(s_in); s_main.wait_stream(s_out)
+        e1.record(s_main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    e2e_run(min(3, args.steps))
     barrier()
-    e2e_steps = timed(args.steps, e2e_step)
+    e2e_ms = e2e_run(args.steps)
     barrier()
-    e2e_ms = sum(e2e_steps)
+    out_host = ohost[0]
 
     # ---- Ulysses configuration (config 3 topology): B = 2 as 2 CFG groups x Ulysses N/2
     ulysses = None

@@ -32,6 +32,17 @@
 
 namespace blade {
 
+#ifdef BLADE_TRACE
+#define TRACE(role, ev, n)                                                                          \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && lane == 0 && (n) < 256) p.trace[((role)*8 + (ev)) * 256 + (n)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, ev, n) \
+  do {                     \
+  } while (0)
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kBlockN = 128;
 constexpr int kThreads = 384;
@@ -59,7 +70,7 @@ struct SmemLayout {
 
 struct Misc {
   uint64_t q_full[2], q_empty[2];
-  uint64_t s_full[2], p_full[2], o_full[2];
+  uint64_t s_full[2], p_lo[2], p_hi[2], o_full[2];  // P is handed over in two 64-key halves
   uint64_t kv_full[10], kv_empty[10];
   uint32_t tmem_base;
   uint32_t pad;
@@ -83,6 +94,7 @@ struct AttnParams {
   float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
   float gap;               // float(sample_gap) for the non-emulated merge
   int exact_merge;
+  long long* trace;  // BLADE_TRACE builds: clock64 stamps of CTA 0 (tools/trace_attn.py)
 };
 
 template <bool IS_BF16>
@@ -131,7 +143,8 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&mz->q_full[t], 1);
       mbar_init(&mz->q_empty[t], 1);
       mbar_init(&mz->s_full[t], 1);
-      mbar_init(&mz->p_full[t], kSoftmaxThreads / 32);  // one arrival per softmax warp
+      mbar_init(&mz->p_lo[t], kSoftmaxThreads / 32);  // one arrival per softmax warp
+      mbar_init(&mz->p_hi[t], kSoftmaxThreads / 32);
       mbar_init(&mz->o_full[t], 1);
     }
     for (int s = 0; s < kStages; ++s) {
@@ -261,6 +274,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto issue_qk = [&](int t, bool last) {
         mbar_wait(&mz->kv_full[slot], ph);
         tc_fence_after();
+        TRACE(2 + t, 2, g[t]);
         if (elect_one()) {
           const uint64_t adesc = make_smem_desc(sQ_addr + t * kTileBytes, 16, 1024, 2);
           const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, 16, 1024, 2);
@@ -279,17 +293,29 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       };
       auto issue_pv = [&](int t, bool fresh) {
-        mbar_wait(&mz->p_full[t], g[t] & 1);
+        // split-P: the PV GEMM over keys 0..63 is issued as soon as the first half of P is in TMEM, while the
+        // softmax warpgroup still exponentiates keys 64..127
+        mbar_wait(&mz->p_lo[t], g[t] & 1);
+        TRACE(2 + t, 0, g[t]);
         mbar_wait(&mz->kv_full[slot], ph);
         tc_fence_after();
+        TRACE(2 + t, 1, g[t]);
+        // V tile [kv 128][D] as D/64 sub-tiles [128][64]; MN-major B: LBO = sub-tile stride, SBO = 8 kv rows
+        const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, kBlockN * 128, 1024, 2);
+        const uint32_t tP = tmem_base + t * kBlockN;
+        const uint32_t tO = tmem_base + 2 * kBlockN + t * D;
         if (elect_one()) {
-          // V tile [kv 128][D] as D/64 sub-tiles [128][64]; MN-major B: LBO = sub-tile stride, SBO = 8 kv rows
-          const uint64_t bdesc = make_smem_desc(sKV_addr + slot * kTileBytes, kBlockN * 128, 1024, 2);
-          const uint32_t tP = tmem_base + t * kBlockN;
-          const uint32_t tO = tmem_base + 2 * kBlockN + t * D;
 #pragma unroll
-          for (int k = 0; k < kBlockN / 16; ++k)
+          for (int k = 0; k < kBlockN / 32; ++k)
             umma_ts(tO, tP + k * 8, bdesc + k * (16 * 128 / 16), idesc_pv, (!fresh) || k > 0);
+        }
+        __syncwarp();
+        mbar_wait(&mz->p_hi[t], g[t] & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = kBlockN / 32; k < kBlockN / 16; ++k)
+            umma_ts(tO, tP + k * 8, bdesc + k * (16 * 128 / 16), idesc_pv, 1);
           tc_commit(&mz->kv_empty[slot]);
           tc_commit(&mz->o_full[t]);
         }
@@ -346,10 +372,12 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = 0; j < ntile; ++j, ++g) {
           mbar_wait(&mz->s_full[t], g & 1);
           tc_fence_after();
+          if (wq == 0) TRACE(t, 0, g);
           uint32_t s[4][32];
 #pragma unroll
           for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
           tmem_wait_ld();
+          if (wq == 0) TRACE(t, 1, g);
           const int valid = (j == ntile - 1) ? tail_valid : kBlockN;
           float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max chains
           if (valid < kBlockN) {
@@ -389,6 +417,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               m = m_new;
             }
           }
+          if (wq == 0) TRACE(t, 2, g);
           const float neg_m = -m;
           float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent sum chains
 #pragma unroll
@@ -406,12 +435,20 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }
             tmem_st16(tS + c * 16, pk);
+            if (c == 1) {  // first 64 keys of P are complete: let the tensor core start on them
+              tmem_wait_st();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&mz->p_lo[t]);
+            }
           }
           l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          if (wq == 0) TRACE(t, 3, g);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&mz->p_full[t]);
+          if (lane == 0) mbar_arrive(&mz->p_hi[t]);
+          if (wq == 0) TRACE(t, 4, g);
         }
         // ---- phase finalisation: the last PV of this phase has to retire first
         mbar_wait(&mz->o_full[t], (g - 1) & 1);
@@ -629,6 +666,10 @@ static int make_tmap(CUtensorMap* map, const BladeTensor* t) {
                    t->stride[1], t->stride[2]);
 }
 
+#ifdef BLADE_TRACE
+static long long* g_trace_buf = nullptr;
+#endif
+
 static int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -718,6 +759,15 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.gap = (float)sample_gap;
   p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;
   p.exact_merge = exact_merge;
+#ifdef BLADE_TRACE
+  {
+    static long long* tbuf = nullptr;  // debug build only (tools/trace_attn.py); the product never allocates
+    if (!tbuf) cudaMalloc(&tbuf, 4 * 8 * 256 * sizeof(long long));
+    cudaMemsetAsync(tbuf, 0, 4 * 8 * 256 * sizeof(long long), stream);
+    p.trace = tbuf;
+    g_trace_buf = tbuf;
+  }
+#endif
 
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
   StageTimer timer(3, stream);
@@ -773,6 +823,13 @@ extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, co
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
                      exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef BLADE_TRACE
+extern "C" int blade_debug_trace(long long* host_out) {
+  if (!g_trace_buf) return 1;
+  return cudaMemcpy(host_out, g_trace_buf, 4 * 8 * 256 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+#endif
 
 extern "C" int blade_probe_qk(const void* q_tile, const void* k_tile, float* s_out, int32_t D, void* stream) {
   return launch_probe(q_tile, k_tile, nullptr, s_out, D, 0, static_cast<cudaStream_t>(stream));
