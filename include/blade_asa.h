@@ -107,6 +107,16 @@ int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const BladeTensor
 int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores,
                               int64_t B, int64_t H, int64_t nb, int64_t D, void* stream);
 
+/* ---- a4 + a5: the reference's sampled-max estimator (efficient_attn_with_pooling, W:62-87 -> P:201-253) -----
+ * blade_asa_sample_tokens: q_off/k_off device int32 [B,H,32] = intra-block offsets of the sampled tokens (the
+ *   reference draws them with torch.rand + topk per call, W:49-51: same offsets for every block of a (b,h));
+ *   q_s/k_s: contiguous [B,H,nb*32,D] outputs (ragged last block padded by replicating the last token, W:35).
+ * blade_asa_scores_sampled: fp32 [B,H,nb,nb] holding the reference's q.dtype-rounded Po (nb <= 256). */
+int blade_asa_sample_tokens(const BladeTensor* q, const BladeTensor* k, const int32_t* q_off, const int32_t* k_off,
+                            void* q_s, void* k_s, int32_t block_size, void* stream);
+int blade_asa_scores_sampled(const void* q_s, const void* k_s, float* scores, int64_t B, int64_t H, int64_t nb,
+                             int64_t D, int32_t dtype, void* stream);
+
 /* ---- a6: energy-threshold block selection ---------------------------------------------------
  * scores fp32 [B,H,nq,nk] -> idx int32 [B,H,nq,nk] (ascending block ids, -1 padded),
  * cnt int32 [B,H,nq], optional mask u8 [B,H,nq,nk], optional kcut int32 [B,H,nq].

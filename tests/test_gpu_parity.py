@@ -307,3 +307,38 @@ def test_full_size_wan_head_properties():
     s = (qa[0, 0, i * 128:(i + 1) * 128].float() @ ka[0, 0, cols].float().T) / D ** 0.5
     _close(l1[0, 0, i * 128:(i + 1) * 128], torch.logsumexp(s, -1), 1e-5, 1e-4)
     _close(o1[0, 0, i * 128:(i + 1) * 128], torch.softmax(s, -1) @ vc[0, 0, cols].float())
+
+
+# ------------------------------------------------------------------ the reference's sampled-max estimator (a4 + a5)
+@pytest.mark.parametrize("flavor,grid,T,H,D", [("wan", (26, 15, 4), 0, 2, 128), ("cog", (15, 10, 6), 40, 3, 64),
+                                               ("wan", (52, 30, 5), 0, 2, 128)])
+def test_sampled_max_estimator_vs_oracle(flavor, grid, T, H, D):
+    """efficient_attn_with_pooling (W:62-87 -> Triton P) on tcgen05 vs its oracle restatement, same sample offsets.
+    Po is stored in bf16 by the reference; MMA accumulation order may flip a bf16 rounding in a few entries."""
+    S = grid[0] * grid[1] * grid[2] + T
+    q, k, v = O.synth_qkv(1, H, S, D, seed=3, structured=2.0, grid=grid, text_length=T)
+    eng = _engine(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, estimator="sampled_max",
+                  max_retain_ratio=0.3)
+    g = torch.Generator().manual_seed(1)
+    qo = O.draw_sample_offsets(1, H, 128, 32, g)
+    ko = O.draw_sample_offsets(1, H, 128, 32, g)
+    want = O.estimator_sampled_max(q, k, 128, qo, ko).float()
+    got = eng.scores_sampled(q.cuda(), k.cuda(), qo.cuda(), ko.cuda()).cpu()
+    assert not torch.isnan(got).any()
+    assert (got == want).float().mean() >= 0.995
+    assert ((got - want).abs() <= 1.6e-2 * want.abs() + 1e-6).all()          # at most ~2 bf16 ulps anywhere
+    # whole layer in sampled_max mode: selection bit-exact and output within tolerance GIVEN the kernel's scores
+    out, dbg = eng.forward(q.cuda(), k.cuda(), v.cuda(), return_debug=True, sample_offsets=(qo.cuda(), ko.cuda()))
+    cfg = O.ASAConfig(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, max_retain_ratio=0.3,
+                      sample_gap=30 if flavor == "wan" else 15, estimator="sampled_max")
+    ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu())
+    assert torch.equal(dbg["mask"].cpu(), ref.mask)
+    _close(out, ref.out)
+
+
+def test_sampled_offsets_follow_reference_distribution():
+    eng = _engine(estimator="sampled_max")
+    off = eng.draw_offsets(2, 3, torch.device("cuda"))
+    assert off.shape == (2, 3, 32) and off.dtype == torch.int32
+    assert int(off.min()) >= 0 and int(off.max()) < 128
+    assert all(len(set(r.tolist())) == 32 for r in off.reshape(-1, 32).cpu())     # topk -> distinct offsets

@@ -202,6 +202,51 @@ class AsaEngine:
                                                  current_stream()))
         return sc
 
+    # ---- the reference's sampled-max estimator (W:62-87 -> P) ------------------------------
+    def draw_offsets(self, B, H, device, generator=None):
+        """W:49-51: rand[B,H,1,block] -> topk indices; one set of num_keep offsets per (b,h)."""
+        kn = self.knobs
+        rand = torch.rand(B, H, 1, kn.block_size, device=device, generator=generator)
+        return torch.topk(rand, kn.num_keep, dim=3).indices[:, :, 0].to(torch.int32).contiguous()
+
+    def scores_sampled(self, q, k, q_off, k_off):
+        """efficient_attn_with_pooling (W:62-87): fp32 [B,H,nb,nb] holding the q.dtype-rounded Po."""
+        self._require_cuda(q, k, q_off, k_off)
+        B, H, S, D = q.shape
+        kn = self.knobs
+        assert kn.num_keep == 32, "the estimator kernel is built for num_keep = 32 (W:62)"
+        nb = -(-S // kn.block_size)
+        q_s = torch.empty(B, H, nb * 32, D, dtype=q.dtype, device=q.device)
+        k_s = torch.empty_like(q_s)
+        q_off = q_off.to(torch.int32).contiguous()
+        k_off = k_off.to(torch.int32).contiguous()
+        check(self.lib.blade_asa_sample_tokens(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), q_off.data_ptr(),
+                                               k_off.data_ptr(), q_s.data_ptr(), k_s.data_ptr(), kn.block_size,
+                                               current_stream()))
+        sc = torch.empty(B, H, nb, nb, dtype=torch.float32, device=q.device)
+        check(self.lib.blade_asa_scores_sampled(q_s.data_ptr(), k_s.data_ptr(), sc.data_ptr(), B, H, nb, D,
+                                                _lib._dtype_code(q), current_stream()))
+        return sc
+
+    def _forward_staged(self, q, k, v, q_off, k_off, return_debug):
+        """estimator == "sampled_max": the layer as five C-ABI calls (prep, sample+score, select, attention)."""
+        B, H, S, D = q.shape
+        kn = self.knobs
+        rearr = kn.use_rearrange
+        (qr, kr, vr), _, (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=False)
+        if not rearr:
+            qr, kr, vr = q, k, v
+        if q_off is None:
+            q_off = self.draw_offsets(B, H, q.device)
+            k_off = self.draw_offsets(B, H, q.device)
+        sc = self.scores_sampled(qr, kr, q_off, k_off)
+        idx, cnt, mask = self.select(sc, want_mask=return_debug)
+        src = self.src_row(q.device, S)
+        out = self.asa_attn(qr, kr, vr, idx, cnt, kp, vp, dst_row=src)
+        if return_debug:
+            return out, dict(scores=sc, mask=mask, idx=idx, cnt=cnt)
+        return out, cnt
+
     def _park(self, device, D):
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         return self.workspace(device, sms * 2 * (D // 8) * 128 * 16)
@@ -238,7 +283,7 @@ class AsaEngine:
 
     # ---- the whole layer ------------------------------------------------------------------
     def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
-                virtual_rows: Optional[torch.Tensor] = None):
+                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None):
         """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
         token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
         processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous."""
@@ -246,6 +291,11 @@ class AsaEngine:
         B, H, S, D = q.shape
         kn = self.knobs
         dev = q.device
+        if kn.estimator == "sampled_max" and scores is None:
+            if virtual_rows is not None:
+                raise ValueError("sampled_max estimator: the packed Ulysses receive layout is not wired yet")
+            qo, ko = sample_offsets if sample_offsets is not None else (None, None)
+            return self._forward_staged(q, k, v, qo, ko, return_debug)
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
         src = self.src_row(dev, S)

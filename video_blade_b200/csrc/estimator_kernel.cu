@@ -1,0 +1,297 @@
+// estimator_kernel.cu -- the reference's sampled-max block-score estimator (SURVEY 8a rows a4 + a5) on tcgen05.
+//
+// Reference: efficient_attn_with_pooling (W:62-87) = pad_to_multiple (W:25-36) + random_sample_tokens (W:37-60:
+// the SAME num_keep = 32 intra-block offsets for every block, drawn per (b,h) and separately for q and k) +
+// the Triton kernel _attn_fwd (P:87-199, non-causal) + row normalisation (P:250-251).  With
+// s = (q~ . k~) * (1/sqrt(D)) * 1.44269504:
+//     R[r, j]  = max_{c in sampled k-block j} s[r, c]           stored in q.dtype          (P:54-55)
+//     m[r]     = max_j (fp32 value before the cast)                                         (P:52-56)
+//     Po[i, j] = max_{r in sampled q-block i} exp2(R[r, j] - m[r])   stored in q.dtype      (P:72-82, l_i == 1)
+//     Po      /= Po.sum(-1)                                          in q.dtype             (P:250-251)
+// The Triton kernel materialises R (50 MB at Wan size) and makes two passes; here one CTA owns 128 sampled
+// query rows (= 4 q-blocks) of one head, streams all sampled keys through a TMA ring, keeps R for its rows in
+// shared memory (bf16, 128 x nb) and never touches HBM for it.
+//
+//   sample_tokens_kernel   gather of the sampled rows into contiguous [B,H,nb*32,D] tensors (replicate padding
+//                          of the ragged last block = clamped row index)
+//   sampled_score_kernel   warps 0-3: TMEM -> registers, 32-column segment maxima, running row max, R to smem,
+//                          final exp2 / block max / normalisation;  warp 4: TMA producer;  warp 5: MMA issuer
+//                          (S = Q~ K~^T, 128x128x D, S double-buffered in TMEM)
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace blade {
+
+constexpr int kKeep = 32;   // sampled tokens per block (W:62)
+constexpr int kTileR = 128; // sampled rows / keys per MMA tile = 4 blocks
+
+struct Strides3e {
+  int64_t b, h, s;
+};
+
+// grid (nb, H, B), 256 threads: 32 sampled rows of q and of k per block, 16-byte chunks
+template <int D>
+__global__ void __launch_bounds__(256) sample_tokens_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                            Strides3e sq, Strides3e sk, const int32_t* __restrict__ q_off,
+                                                            const int32_t* __restrict__ k_off, uint16_t* __restrict__ q_s,
+                                                            uint16_t* __restrict__ k_s, int S, int H, int nb, int block) {
+  constexpr int LPR = D / 8;
+  const int blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int64_t bh = static_cast<int64_t>(b) * H + h;
+  for (int e = threadIdx.x; e < 2 * kKeep * LPR; e += 256) {
+    const int t = e / (kKeep * LPR);           // 0 = q, 1 = k
+    const int r = (e / LPR) % kKeep, chunk = e % LPR;
+    const int off = __ldg((t ? k_off : q_off) + bh * kKeep + r);
+    int row = blk * block + off;
+    row = row < S ? row : S - 1;                // replicate padding (W:35)
+    const Strides3e st = t ? sk : sq;
+    const uint16_t* src = (t ? k : q) + b * st.b + h * st.h + static_cast<int64_t>(row) * st.s;
+    uint16_t* dst = (t ? k_s : q_s) + ((bh * nb + blk) * kKeep + r) * D;
+    reinterpret_cast<uint4*>(dst)[chunk] = __ldg(reinterpret_cast<const uint4*>(src) + chunk);
+  }
+}
+
+template <int D>
+struct EstSmem {
+  static constexpr int kTileBytes = kTileR * D * 2;
+  static constexpr int kStages = D == 128 ? 4 : 6;
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = kTileBytes;
+  static constexpr int kROff = kKOff + kStages * kTileBytes;
+  static constexpr int kRStride = 258;               // padded row (129 words): conflict-free per-row access
+  static constexpr int kRBytes = kTileR * kRStride * 2;  // nb <= 256
+  static constexpr int kMiscOff = kROff + kRBytes;
+  static constexpr int kTotal = kMiscOff + 256 + 1024;
+};
+
+struct EstMisc {
+  uint64_t q_full, k_full[6], k_empty[6], s_full[2], s_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int D, bool IS_BF16>
+__global__ void __launch_bounds__(192, 1)
+sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     float* __restrict__ scores, int nb, float scale_log2) {
+  using L = EstSmem<D>;
+  constexpr int kStages = L::kStages;
+  constexpr int kTileBytes = L::kTileBytes;
+  constexpr int kSub = D / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + L::kQOff;
+  uint8_t* sK = smem + L::kKOff;
+  uint16_t* sR = reinterpret_cast<uint16_t*>(smem + L::kROff);  // [128 rows][258] bf16/f16 bits
+  EstMisc* mz = reinterpret_cast<EstMisc*>(smem + L::kMiscOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nkt = (nb + 3) / 4;  // key tiles of 4 blocks
+
+  if (threadIdx.x == 0) {
+    mbar_init(&mz->q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&mz->k_full[s], 1);
+      mbar_init(&mz->k_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&mz->s_full[i], 1);
+      mbar_init(&mz->s_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<256>(&mz->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = mz->tmem_base;
+
+  if (warp == 4) {
+    // ------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&mz->q_full, kTileBytes);
+      for (int dh = 0; dh < kSub; ++dh)
+        tma_load_4d(sQ + dh * (kTileR * 128), &tmQ, &mz->q_full, dh * 64, qt * kTileR, h, b, kEvictFirst);
+    }
+    __syncwarp();
+    uint32_t slot = 0, ph = 0;
+    for (int jt = 0; jt < nkt; ++jt) {
+      mbar_wait(&mz->k_empty[slot], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&mz->k_full[slot], kTileBytes);
+        for (int dh = 0; dh < kSub; ++dh)
+          tma_load_4d(sK + slot * kTileBytes + dh * (kTileR * 128), &tmK, &mz->k_full[slot], dh * 64, jt * kTileR, h,
+                      b, kEvictLast);
+      }
+      __syncwarp();
+      if (++slot == kStages) {
+        slot = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(kTileR, kTileR, IS_BF16, false, false);
+    const uint32_t sQ_addr = smem_u32(sQ), sK_addr = smem_u32(sK);
+    mbar_wait(&mz->q_full, 0);
+    uint32_t slot = 0, ph = 0;
+    for (int jt = 0; jt < nkt; ++jt) {
+      const int bsel = jt & 1;
+      mbar_wait(&mz->s_empty[bsel], ((jt >> 1) & 1) ^ 1);  // the reducers have drained this S buffer
+      mbar_wait(&mz->k_full[slot], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_smem_desc(sQ_addr, 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sK_addr + slot * kTileBytes, 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t koff = static_cast<uint32_t>((k >> 2) * (kTileR * 128 / 16) + (k & 3) * 2);
+          umma_ss(tmem_base + bsel * kTileR, adesc + koff, bdesc + koff, idesc, k > 0);
+        }
+        tc_commit(&mz->k_empty[slot]);
+        tc_commit(&mz->s_full[bsel]);
+      }
+      __syncwarp();
+      if (++slot == kStages) {
+        slot = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ reducers: one sampled query row per thread
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint16_t* myR = sR + row * L::kRStride;
+    float m = -INFINITY;
+    for (int jt = 0; jt < nkt; ++jt) {
+      const int bsel = jt & 1;
+      mbar_wait(&mz->s_full[bsel], (jt >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_base + lane_base + bsel * kTileR + c * 32, s[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mz->s_empty[bsel]);  // S is in registers: the buffer can be overwritten
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+        }
+        const int j = jt * 4 + c;
+        float bm = fmaxf(mx0, mx1) * scale_log2;  // P:52 `tl.max(qk, 1) * qk_scale`
+        if (j >= nb) bm = -INFINITY;              // zero-filled key blocks beyond the sequence
+        m = fmaxf(m, bm);
+        if (j < 256) myR[j] = IS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(bm)) : __half_as_ushort(__float2half_rn(bm));
+      }
+    }
+    // Po[i, j] = max over the 32 rows of q-block i (= this warp) of exp2(R[r,j] - m[r]); lane j%32 keeps column j
+    const int qblk = qt * 4 + warp;
+    float po[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) po[jj] = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j0 = jj * 32;
+      if (j0 >= nb) break;
+      float keep = 0.f;
+      for (int jl = 0; jl < 32; ++jl) {
+        const int j = j0 + jl;
+        if (j >= nb) break;
+        const float r = IS_BF16 ? __bfloat162float(__ushort_as_bfloat16(myR[j])) : __half2float(__ushort_as_half(myR[j]));
+        float e = ex2_approx(r - m);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, off));
+        if (jl == lane) keep = e;
+      }
+      keep = IS_BF16 ? bf16_round(keep) : __half2float(__float2half_rn(keep));  // Po is stored in q.dtype (P:80)
+      po[jj] = keep;
+      if (j0 + lane < nb) sum += keep;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    // P:250-251 in q.dtype: Sum = sum(Po) (fp32 accumulate, rounded), Po /= Sum (rounded)
+    const float sum_r = IS_BF16 ? bf16_round(sum) : __half2float(__float2half_rn(sum));
+    if (qblk < nb) {
+      float* out = scores + ((static_cast<int64_t>(b) * gridDim.y + h) * nb + qblk) * nb;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = jj * 32 + lane;
+        if (j < nb) {
+          const float v = po[jj] / sum_r;
+          out[j] = IS_BF16 ? bf16_round(v) : __half2float(__float2half_rn(v));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace blade
+
+using namespace blade;
+
+extern "C" int blade_asa_sample_tokens(const BladeTensor* q, const BladeTensor* k, const int32_t* q_off,
+                                       const int32_t* k_off, void* q_s, void* k_s, int32_t block_size, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_tensor16(q, "q")) return e;
+  if (int e = check_tensor16(k, "k")) return e;
+  BLADE_REQUIRE(q_off && k_off && q_s && k_s, BLADE_ERR_ARG, "null pointer");
+  BLADE_REQUIRE(block_size == 64 || block_size == 128, BLADE_ERR_ARG, "block_size %d not in {64,128}", block_size);
+  const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
+  for (int i = 0; i < 4; ++i) BLADE_REQUIRE(k->shape[i] == q->shape[i], BLADE_ERR_SHAPE, "q/k shapes differ");
+  const int nb = static_cast<int>(ceil_div(S, block_size));
+  Strides3e sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]};
+  dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
+  if (D == 128)
+    sample_tokens_kernel<128><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(q->ptr), static_cast<const uint16_t*>(k->ptr), sq, sk,
+                                                        q_off, k_off, static_cast<uint16_t*>(q_s), static_cast<uint16_t*>(k_s),
+                                                        (int)S, (int)H, nb, block_size);
+  else
+    sample_tokens_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(q->ptr), static_cast<const uint16_t*>(k->ptr), sq, sk,
+                                                       q_off, k_off, static_cast<uint16_t*>(q_s), static_cast<uint16_t*>(k_s),
+                                                       (int)S, (int)H, nb, block_size);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+extern "C" int blade_asa_scores_sampled(const void* q_s, const void* k_s, float* scores, int64_t B, int64_t H, int64_t nb,
+                                        int64_t D, int32_t dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(q_s && k_s && scores, BLADE_ERR_ARG, "null pointer");
+  BLADE_REQUIRE(D == 64 || D == 128, BLADE_ERR_SHAPE, "head dim %lld not in {64,128}", (long long)D);
+  BLADE_REQUIRE(nb >= 1 && nb <= 256, BLADE_ERR_SHAPE, "sampled estimator supports nb <= 256 blocks (got %lld)", (long long)nb);
+  BLADE_REQUIRE(dtype == BLADE_BF16 || dtype == BLADE_F16, BLADE_ERR_DTYPE, "dtype");
+  const int64_t Ss = nb * kKeep;
+  CUtensorMap tmQ, tmK;
+  if (int e = make_tmap(&tmQ, q_s, dtype, B, H, Ss, D, H * Ss * D, Ss * D, D)) return e;
+  if (int e = make_tmap(&tmK, k_s, dtype, B, H, Ss, D, H * Ss * D, Ss * D, D)) return e;
+  StageTimer timer(1, stream);
+  dim3 grid(static_cast<unsigned>(ceil_div(nb, 4)), static_cast<unsigned>(H), static_cast<unsigned>(B));
+  const float scale_log2 = (1.0f / sqrtf(static_cast<float>(D))) * 1.44269504f;  // P:163 literal
+#define LAUNCH_EST(DD, BF)                                                                                          \
+  do {                                                                                                              \
+    auto kern = sampled_score_kernel<DD, BF>;                                                                       \
+    BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EstSmem<DD>::kTotal));    \
+    kern<<<grid, 192, EstSmem<DD>::kTotal, stream>>>(tmQ, tmK, scores, (int)nb, scale_log2);                        \
+  } while (0)
+  const bool bf = dtype == BLADE_BF16;
+  if (D == 128) { if (bf) LAUNCH_EST(128, true); else LAUNCH_EST(128, false); }
+  else          { if (bf) LAUNCH_EST(64, true); else LAUNCH_EST(64, false); }
+#undef LAUNCH_EST
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
