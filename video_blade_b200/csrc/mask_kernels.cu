@@ -380,6 +380,139 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   if (lane == 0) cnt[row] = base;
 }
 
+// ------------------------------------------------------------------------------------------------
+// select (nk <= 256): one warp per score row, E = elements per lane (nk <= 32*E).  The row is sorted by a
+// bitonic network held in registers (position p = lane*E + r; partners with j < E are in-lane, the others one
+// __shfl_xor away) under the total order (value desc, index asc) -- the same order as torch.sort(stable=True),
+// unique keys so the network's instability does not matter.  Then: fp64 sequential prefix sums by lane 0
+// (bit-exact with torch's CPU cumsum), clamp, flag scatter, ballot compaction to the ascending index list.
+// dynamic smem: 8 warps * 2 * 32*E doubles (sorted values as fp64 + int flags).
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __restrict__ scores, int64_t total_rows, int nq,
+                                                             int nk, int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
+                                                             const int32_t* __restrict__ hi_bh, float thr, int force_last,
+                                                             int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
+                                                             uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
+  constexpr int N = 32 * E;
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sorted = reinterpret_cast<double*>(sm) + warp * 2 * N;   // sorted values, widened in parallel
+  int* flag = reinterpret_cast<int*>(sorted + N);                 // flag[original index] = selected
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= total_rows) return;
+  const int qi = static_cast<int>(row % nq);
+  const int64_t bh = row / nq;
+  const float* src = scores + row * nk;
+
+  float v[E];
+  int id[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int p = lane * E + r;
+    v[r] = p < nk ? __ldg(src + p) : -INFINITY;              // padding sorts behind every real entry
+    id[r] = p;
+  }
+  // "a comes before b" in the target order
+  auto before = [](float av, int ai, float bv, int bi) { return (av > bv) || (av == bv && ai < bi); };
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j >= E) {                                          // partner lives in lane ^ (j / E), same r
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const int p = lane * E + r;
+          const float ov = __shfl_xor_sync(0xffffffffu, v[r], j / E);
+          const int oi = __shfl_xor_sync(0xffffffffu, id[r], j / E);
+          const bool up = (p & k) == 0, lower = (p & j) == 0;
+          const bool mine_first = before(v[r], id[r], ov, oi);
+          const bool keep = mine_first == (up == lower);
+          v[r] = keep ? v[r] : ov;
+          id[r] = keep ? id[r] : oi;
+        }
+      } else {                                               // partner is register r ^ j of the same lane
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r & j) == 0) {
+            const int r2 = r | j;
+            const int p = lane * E + r;
+            const bool up = (p & k) == 0;
+            const bool first = before(v[r], id[r], v[r2], id[r2]);
+            const bool swap = first != up;                   // lower slot must hold the "first" element iff up
+            const float tv = v[r];
+            const int ti = id[r];
+            v[r] = swap ? v[r2] : tv;
+            id[r] = swap ? id[r2] : ti;
+            v[r2] = swap ? tv : v[r2];
+            id[r2] = swap ? ti : id[r2];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    sorted[lane * E + r] = static_cast<double>(v[r]);
+    flag[lane * E + r] = 0;
+  }
+  __syncwarp();
+
+  const int lo = lo_bh ? lo_bh[bh] : lo_s;
+  const int hi = hi_bh ? hi_bh[bh] : hi_s;
+  int kfirst = nk;
+  if (lane == 0) {
+    // sequential on purpose (bit-exact with torch's CPU cumsum); the loads are independent of the add chain,
+    // so unrolling lets them run ahead.  Padding entries are -inf only beyond nk and are never added.
+    double acc = 0.0;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 8 <= nk; i += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = sorted[i + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += t[u];
+    }
+    for (; i < nk; ++i) acc += sorted[i];
+    const float total = static_cast<float>(acc);
+    const float th = __fmul_rn(thr, total);
+    acc = 0.0;
+    const int lim = hi < nk ? hi : nk;                       // beyond `hi` the clamp decides
+    for (i = 0; i < lim; ++i) {
+      acc += sorted[i];
+      if (static_cast<float>(acc) >= th) {
+        kfirst = i;
+        break;
+      }
+    }
+  }
+  kfirst = __shfl_sync(0xffffffffu, kfirst, 0);
+  int kc = kfirst < lo ? lo : kfirst;
+  kc = kc > hi ? hi : kc;
+  if (kcut && lane == 0) kcut[row] = kc;
+#pragma unroll
+  for (int r = 0; r < E; ++r)
+    if (lane * E + r < kc && id[r] < nk) flag[id[r]] = 1;    // sorted position < cut  ->  keep that block
+  __syncwarp();
+
+  const bool full_row = force_last > 0 && qi >= nq - force_last;
+  int32_t* irow = idx + row * nk;
+  uint8_t* mrow = mask ? mask + row * nk : nullptr;
+  int base = 0;
+#pragma unroll
+  for (int sblk = 0; sblk < E; ++sblk) {
+    const int j = sblk * 32 + lane;
+    const bool sel = j < nk && (flag[j] != 0 || full_row || (force_last > 0 && j >= nk - force_last));
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    if (sel) irow[base + __popc(bal & ((1u << lane) - 1u))] = j;
+    if (mrow && j < nk) mrow[j] = sel ? 1 : 0;
+    base += __popc(bal);
+  }
+  for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
+  if (lane == 0) cnt[row] = base;
+}
+
 __global__ void __launch_bounds__(256) mask_to_index_kernel(const uint8_t* __restrict__ mask, int64_t total_rows, int nk,
                                                             int32_t* __restrict__ idx, int32_t* __restrict__ cnt) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -496,27 +629,25 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
   const int nk_pad = static_cast<int>((nk + 31) & ~31);
   const size_t smem = 8 * 2 * nk_pad * sizeof(float);
   StageTimer timer(2, stream);
-  const int nslot = nk_pad / 32;
-#define LAUNCH_SELECT(NS)                                                                                          \
+#define LAUNCH_BITONIC(EE)                                                                                       \
   do {                                                                                                             \
-    if (smem > 48 * 1024)                                                                                          \
-      BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    select_kernel<NS><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(                            \
+    const size_t sm_b = 8 * (2 * 32 * EE) * sizeof(double);                                                           \
+    select_bitonic_kernel<EE><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, sm_b, stream>>>(                    \
         scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,     \
         cfg->force_last, idx, cnt, mask_opt, kcut_opt);                                                            \
   } while (0)
-  switch (nslot) {
-    case 1: LAUNCH_SELECT(1); break;
-    case 2: LAUNCH_SELECT(2); break;
-    case 3: LAUNCH_SELECT(3); break;
-    case 4: LAUNCH_SELECT(4); break;
-    case 5: LAUNCH_SELECT(5); break;
-    case 6: LAUNCH_SELECT(6); break;
-    case 7: LAUNCH_SELECT(7); break;
-    case 8: LAUNCH_SELECT(8); break;
-    default: LAUNCH_SELECT(0); break;
+  if (nk <= 32) LAUNCH_BITONIC(1);
+  else if (nk <= 64) LAUNCH_BITONIC(2);
+  else if (nk <= 128) LAUNCH_BITONIC(4);
+  else if (nk <= 256) LAUNCH_BITONIC(8);
+  else {  // long rows: O(n^2) rank counting fallback
+    if (smem > 48 * 1024)
+      BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_kernel<0><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
+        scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
+        cfg->force_last, idx, cnt, mask_opt, kcut_opt);
   }
-#undef LAUNCH_SELECT
+#undef LAUNCH_BITONIC
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
 }
