@@ -139,6 +139,23 @@ int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTensor* k, cons
                                 BladeTensor* out, float* lse, const int32_t* dst_row,
                                 float softmax_scale, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- block_size 64 (BASELINE config 1): 64x64 mask granularity on the 128x128 tensor-core tiles -------------
+ * blade_mask64_to_index: bool mask u8 [B,H,nq64,nk64] -> per 128-row query tile an ascending list of 128-key tiles,
+ *   entry = tile id | (quadrant mask << 28) (bit 2*rowhalf+colhalf); idx int32 [B,H,ceil(nq64/2),ceil(nk64/2)].
+ * blade_block_sparse_attn64_fwd / blade_asa_attn64_fwd: as the block-128 entry points, on such lists. */
+int blade_mask64_to_index(const uint8_t* mask, int64_t B, int64_t H, int64_t nq64, int64_t nk64,
+                          int32_t* idx, int32_t* cnt, void* stream);
+int blade_block_sparse_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                  const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                                  BladeTensor* out, float* lse, const int32_t* dst_row,
+                                  float softmax_scale, void* workspace, size_t ws_bytes, void* stream);
+int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                         const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                         const BladeTensor* k_pool, const BladeTensor* v_pool, int32_t sample_gap,
+                         BladeTensor* out, const int32_t* dst_row,
+                         float softmax_scale, int32_t exact_merge,
+                         void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- a8+a10+a11: sparse branch + pooled branch + reference-exact LSE merge, one launch ------- */
 int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
                        const int32_t* idx, const int32_t* cnt, int64_t idx_stride,

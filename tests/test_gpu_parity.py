@@ -342,3 +342,53 @@ def test_sampled_offsets_follow_reference_distribution():
     assert off.shape == (2, 3, 32) and off.dtype == torch.int32
     assert int(off.min()) >= 0 and int(off.max()) < 128
     assert all(len(set(r.tolist())) == 32 for r in off.reshape(-1, 32).cpu())     # topk -> distinct offsets
+
+
+# ------------------------------------------------------------------ block size 64 (BASELINE config 1)
+def test_mask64_to_index_quadrants():
+    eng = _engine(block_size=64, use_rearrange=False)
+    g = torch.Generator().manual_seed(4)
+    m = torch.rand(1, 2, 9, 11, generator=g) < 0.35
+    idx, cnt = eng.mask64_to_index(m.cuda())
+    idx, cnt = idx.cpu(), cnt.cpu()
+    nq, nk = 5, 6
+    mp = torch.zeros(1, 2, 2 * nq, 2 * nk, dtype=torch.bool)
+    mp[:, :, :9, :11] = m
+    for h in range(2):
+        for qt in range(nq):
+            want = []
+            for kt in range(nk):
+                fl = (int(mp[0, h, 2 * qt, 2 * kt]) | int(mp[0, h, 2 * qt, 2 * kt + 1]) << 1
+                      | int(mp[0, h, 2 * qt + 1, 2 * kt]) << 2 | int(mp[0, h, 2 * qt + 1, 2 * kt + 1]) << 3)
+                if fl:
+                    want.append(kt | (fl << 28))
+            got = [int(x) & 0xFFFFFFFF for x in idx[0, h, qt, : int(cnt[0, h, qt])]]
+            assert got == want
+
+
+@pytest.mark.parametrize("S,H", [(7800, 2), (1000, 1)])
+def test_block64_attention_vs_oracle(S, H):
+    """64x64 block mask (config 1 granularity): sparse branch alone, and the full layer at 52x30x5 = 7800 tokens."""
+    eng = _engine(block_size=64, use_rearrange=False)
+    q, k, v = O.synth_qkv(1, H, S, 128, seed=S)
+    nb = -(-S // 64)
+    mask = _rand_mask(1, H, nb, nb, 0.2, seed=S + 3)
+    idx, cnt = eng.mask64_to_index(mask.cuda())
+    out, lse = eng.block_sparse_attn(q.cuda(), k.cuda(), v.cuda(), idx, cnt, sub64=True)
+    wout, wlse = O.dense_masked_attention(q, k, v, mask, block_q=64)
+    _close(out, wout)
+    _close(lse, wlse, 1e-5, 1e-4)
+
+
+def test_block64_layer_config1():
+    grid = (52, 30, 5)
+    S, H, D = 7800, 2, 128
+    q, k, v = O.synth_qkv(1, H, S, D, seed=17, structured=2.0, grid=grid)
+    eng = _engine(width=grid[0], height=grid[1], depth=grid[2], block_size=64)
+    out, dbg = eng.forward(q.cuda(), k.cuda(), v.cuda(), return_debug=True)
+    cfg = O.ASAConfig.wan(width=grid[0], height=grid[1], depth=grid[2], block_size=64)
+    assert dbg["scores"].shape[-1] == 122
+    want_mask, _ = O.select_mask(dbg["scores"].cpu(), cfg)
+    assert torch.equal(dbg["mask"].cpu(), want_mask)
+    ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu())
+    _close(out, ref.out)

@@ -33,6 +33,7 @@ SYMBOLS = [
     "blade_asa_workspace_bytes", "blade_asa_prep", "blade_asa_scores_meanpool", "blade_asa_select",
     "blade_mask_to_index", "blade_block_sparse_attn_fwd", "blade_asa_attn_fwd", "blade_asa_forward",
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
+    "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -66,6 +67,9 @@ def load() -> C.CDLL:
     lib.blade_profile_events.argtypes = [i32, vp, vp]
     lib.blade_probe_qk.argtypes = [vp, vp, vp, i32, vp]
     lib.blade_probe_pv.argtypes = [vp, vp, vp, i32, vp]
+    lib.blade_mask64_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
+    lib.blade_block_sparse_attn64_fwd.argtypes = lib.blade_block_sparse_attn_fwd.argtypes
+    lib.blade_asa_attn64_fwd.argtypes = lib.blade_asa_attn_fwd.argtypes
     lib.blade_asa_sample_tokens.argtypes = [T, T, vp, vp, vp, vp, i32, vp]
     lib.blade_asa_scores_sampled.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, vp]
     if hasattr(lib, "blade_rope_pack"):

@@ -228,20 +228,34 @@ class AsaEngine:
                                                 _lib._dtype_code(q), current_stream()))
         return sc
 
-    def _forward_staged(self, q, k, v, q_off, k_off, return_debug):
-        """estimator == "sampled_max": the layer as five C-ABI calls (prep, sample+score, select, attention)."""
+    def _forward_staged(self, q, k, v, q_off, k_off, return_debug, scores=None):
+        """The layer as separate C-ABI calls (prep, score, select, attention): used for estimator ==
+        "sampled_max" and for block_size 64 (blade_asa_forward covers the default block-128 mean-pool path)."""
         B, H, S, D = q.shape
         kn = self.knobs
         rearr = kn.use_rearrange
-        (qr, kr, vr), _, (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=False)
+        sampled = kn.estimator == "sampled_max" and scores is None
+        (qr, kr, vr), (qm, km), (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=not sampled and scores is None)
         if not rearr:
             qr, kr, vr = q, k, v
-        if q_off is None:
-            q_off = self.draw_offsets(B, H, q.device)
-            k_off = self.draw_offsets(B, H, q.device)
-        sc = self.scores_sampled(qr, kr, q_off, k_off)
-        idx, cnt, mask = self.select(sc, want_mask=return_debug)
+        if scores is not None:
+            sc = scores
+        elif sampled:
+            if q_off is None:
+                q_off = self.draw_offsets(B, H, q.device)
+                k_off = self.draw_offsets(B, H, q.device)
+            sc = self.scores_sampled(qr, kr, q_off, k_off)
+        else:
+            sc = self.scores_meanpool(qm, km)
         src = self.src_row(q.device, S)
+        if kn.block_size == 64:
+            idx64, cnt64, mask = self.select(sc, want_mask=True)
+            idx, cnt = self.mask64_to_index(mask)
+            out = self.asa_attn(qr, kr, vr, idx, cnt, kp, vp, dst_row=src, sub64=True)
+            if return_debug:
+                return out, dict(scores=sc, mask=mask, idx=idx, cnt=cnt64)
+            return out, cnt64
+        idx, cnt, mask = self.select(sc, want_mask=return_debug)
         out = self.asa_attn(qr, kr, vr, idx, cnt, kp, vp, dst_row=src)
         if return_debug:
             return out, dict(scores=sc, mask=mask, idx=idx, cnt=cnt)
@@ -251,7 +265,7 @@ class AsaEngine:
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         return self.workspace(device, sms * 2 * (D // 8) * 128 * 16)
 
-    def block_sparse_attn(self, q, k, v, idx, cnt, out=None, dst_row=None, want_lse=True):
+    def block_sparse_attn(self, q, k, v, idx, cnt, out=None, dst_row=None, want_lse=True, sub64=False):
         """block_sparse_attn(q,k,v,block_mask) (W:278-309) on an index list; returns (out, lse fp32 [B,H,S])."""
         self._require_cuda(q, k, v, idx, cnt)
         B, H, S, D = q.shape
@@ -260,13 +274,26 @@ class AsaEngine:
         lse = torch.empty(B, H, S, dtype=torch.float32, device=q.device) if want_lse else None
         ws = self._park(q.device, D)
         od = tensor_desc(out)
-        check(self.lib.blade_block_sparse_attn_fwd(
+        fn = self.lib.blade_block_sparse_attn64_fwd if sub64 else self.lib.blade_block_sparse_attn_fwd
+        check(fn(
             C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), idx.data_ptr(), cnt.data_ptr(),
             idx.shape[-1], C.byref(od), ptr(lse), ptr(dst_row), 1.0 / math.sqrt(D), ws.data_ptr(), ws.numel(),
             current_stream()))
         return out, lse
 
-    def asa_attn(self, q, k, v, idx, cnt, k_pool, v_pool, out=None, dst_row=None, exact_merge=None):
+    def mask64_to_index(self, mask64: torch.Tensor):
+        """block_size 64: bool mask [B,H,nq64,nk64] -> quadrant-flagged list over 128x128 tiles."""
+        self._require_cuda(mask64)
+        m = mask64.to(torch.uint8).contiguous()
+        B, H, nq64, nk64 = m.shape
+        nq, nk = -(-nq64 // 2), -(-nk64 // 2)
+        idx = torch.empty(B, H, nq, nk, dtype=torch.int32, device=m.device)
+        cnt = torch.empty(B, H, nq, dtype=torch.int32, device=m.device)
+        check(self.lib.blade_mask64_to_index(m.data_ptr(), B, H, nq64, nk64, idx.data_ptr(), cnt.data_ptr(),
+                                             current_stream()))
+        return idx, cnt
+
+    def asa_attn(self, q, k, v, idx, cnt, k_pool, v_pool, out=None, dst_row=None, exact_merge=None, sub64=False):
         """Sparse branch + pooled branch + merge (W:343-370) in one launch."""
         self._require_cuda(q, k, v, idx, cnt, k_pool, v_pool)
         B, H, S, D = q.shape
@@ -274,7 +301,8 @@ class AsaEngine:
             out = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
         ws = self._park(q.device, D)
         em = self.knobs.exact_merge if exact_merge is None else exact_merge
-        check(self.lib.blade_asa_attn_fwd(
+        fn = self.lib.blade_asa_attn64_fwd if sub64 else self.lib.blade_asa_attn_fwd
+        check(fn(
             C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), idx.data_ptr(), cnt.data_ptr(),
             idx.shape[-1], C.byref(tensor_desc(k_pool)), C.byref(tensor_desc(v_pool)), self.knobs.sample_gap,
             C.byref(tensor_desc(out)), ptr(dst_row), 1.0 / math.sqrt(D), 1 if em else 0, ws.data_ptr(), ws.numel(),
@@ -291,11 +319,11 @@ class AsaEngine:
         B, H, S, D = q.shape
         kn = self.knobs
         dev = q.device
-        if kn.estimator == "sampled_max" and scores is None:
+        if (kn.estimator == "sampled_max" and scores is None) or kn.block_size == 64:
             if virtual_rows is not None:
-                raise ValueError("sampled_max estimator: the packed Ulysses receive layout is not wired yet")
+                raise ValueError("staged path (sampled_max / block 64): the packed Ulysses receive layout is not wired yet")
             qo, ko = sample_offsets if sample_offsets is not None else (None, None)
-            return self._forward_staged(q, k, v, qo, ko, return_debug)
+            return self._forward_staged(q, k, v, qo, ko, return_debug, scores=scores)
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
         src = self.src_row(dev, S)

@@ -95,6 +95,7 @@ struct AttnParams {
   float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
   float gap;               // float(sample_gap) for the non-emulated merge
   int exact_merge;
+  int sub64;  // 1: list entries carry a 4-bit quadrant mask in bits 28..31 (64x64 mask granularity on 128x128 tiles)
   long long* trace;  // BLADE_TRACE builds: clock64 stamps of CTA 0 (tools/trace_attn.py)
 };
 
@@ -193,7 +194,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         lists[t] = p.idx + row * p.idx_stride;
         // cooperative, coalesced fetch of the block-id list into smem (private to this warp)
         for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32)
-          mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j));
+          mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j) & 0x0FFFFFFF);
       }
       __syncwarp();
 #pragma unroll
@@ -219,7 +220,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           row = j * kBlockN;
         } else {
           const int jj = j - npt;
-          const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : __ldg(lists[t] + jj);
+          const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : (__ldg(lists[t] + jj) & 0x0FFFFFFF);
           map = is_v ? &tmV : &tmK;
           row = kb * kBlockN;
         }
@@ -362,7 +363,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (qb >= p.nq) continue;
       const int64_t lrow = static_cast<int64_t>(bh) * p.nq + qb;
       const int ns = __ldg(p.cnt + lrow);
-      const int last_kb = ns > 0 ? __ldg(p.idx + lrow * p.idx_stride + ns - 1) : -1;
+      const int last_kb = ns > 0 ? (__ldg(p.idx + lrow * p.idx_stride + ns - 1) & 0x0FFFFFFF) : -1;
       const int sparse_tail = (last_kb == p.nk - 1) ? seq_tail : kBlockN;
       float lse2 = 0.f;
 
@@ -381,12 +382,16 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (wq == 0) TRACE(t, 1, g);
           const int valid = (j == ntile - 1) ? tail_valid : kBlockN;
           float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max chains
-          if (valid < kBlockN) {
+          // 64x64 mask granularity (block_size 64): bits (2*rowhalf + colhalf) of the entry's quadrant mask
+          unsigned cmask = 3u;
+          if (p.sub64 && phase == 1)
+            cmask = (static_cast<unsigned>(__ldg(p.idx + lrow * p.idx_stride + j)) >> (28 + 2 * (wq >> 1))) & 3u;
+          if (valid < kBlockN || cmask != 3u) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+                if (c * 32 + i >= valid || !((cmask >> (c >> 1)) & 1u)) s[c][i] = __float_as_uint(-INFINITY);
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -396,6 +401,8 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sl2;
           if (j == 0) {
             m = mx;
+          } else if (m == -INFINITY) {
+            m = mx;  // every earlier tile was fully masked for this row half (sub64 lists): O and l are still 0
           } else {
             const float m_cand = fmaxf(m, mx);
             const bool need = (m_cand - m) > kRescaleThresh;
@@ -419,7 +426,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           if (wq == 0) TRACE(t, 2, g);
-          const float neg_m = -m;
+          const float neg_m = (m == -INFINITY) ? 0.f : -m;  // all-masked so far: exp2(-inf - 0) = 0, never NaN
           float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent sum chains
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -630,6 +637,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #ifdef BLADE_TRACE
 static long long* g_trace_buf = nullptr;
 #endif
+static thread_local int g_sub64_next = 0;  // set by blade_block_sparse_attn64_fwd / blade_asa_attn64_fwd for one launch
 
 static int device_sm_count() {
   static int n = 0;
@@ -720,6 +728,8 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.gap = (float)sample_gap;
   p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;
   p.exact_merge = exact_merge;
+  p.sub64 = g_sub64_next;
+  g_sub64_next = 0;
 #ifdef BLADE_TRACE
   {
     static long long* tbuf = nullptr;  // debug build only (tools/trace_attn.py); the product never allocates
@@ -773,6 +783,26 @@ extern "C" int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTens
                                            void* workspace, size_t ws_bytes, void* stream) {
   return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
                      ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// block_size 64 variants: idx entries = (128-key tile id) | (quadrant mask << 28), built by blade_mask64_to_index
+extern "C" int blade_block_sparse_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                             const int32_t* idx, const int32_t* cnt, int64_t idx_stride,
+                                             BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
+                                             void* workspace, size_t ws_bytes, void* stream) {
+  g_sub64_next = 1;
+  return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
+                     ws_bytes, static_cast<cudaStream_t>(stream));
+}
+extern "C" int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
+                                    const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool,
+                                    const BladeTensor* v_pool, int32_t sample_gap, BladeTensor* out,
+                                    const int32_t* dst_row, float softmax_scale, int32_t exact_merge, void* workspace,
+                                    size_t ws_bytes, void* stream) {
+  BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
+  g_sub64_next = 1;
+  return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,

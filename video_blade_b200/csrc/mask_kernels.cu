@@ -532,6 +532,42 @@ __global__ void __launch_bounds__(256) mask_to_index_kernel(const uint8_t* __res
   if (lane == 0) cnt[row] = base;
 }
 
+// 64-granular bool mask [rows64][nk64] -> per 128-row query tile: ascending list of 128-key tiles that contain at
+// least one selected 64x64 block, each entry = tile id | (quadrant mask << 28), quadrant bit = 2*rowhalf + colhalf.
+// One warp per query tile.
+__global__ void __launch_bounds__(256) mask64_to_index_kernel(const uint8_t* __restrict__ mask, int64_t total_tiles, int nq64,
+                                                              int nk64, int nq128, int nk128, int32_t* __restrict__ idx,
+                                                              int32_t* __restrict__ cnt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tile = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (tile >= total_tiles) return;
+  const int qt = static_cast<int>(tile % nq128);
+  const int64_t bh = tile / nq128;
+  const uint8_t* m0 = mask + (bh * nq64 + 2 * qt) * nk64;
+  const bool has1 = 2 * qt + 1 < nq64;
+  const uint8_t* m1 = m0 + nk64;
+  int32_t* irow = idx + tile * nk128;
+  int base = 0;
+  for (int j0 = 0; j0 < nk128; j0 += 32) {
+    const int kt = j0 + lane;
+    unsigned fl = 0;
+    if (kt < nk128) {
+      const int c0 = 2 * kt, c1 = 2 * kt + 1;
+      fl |= m0[c0] ? 1u : 0u;
+      if (c1 < nk64) fl |= m0[c1] ? 2u : 0u;
+      if (has1) {
+        fl |= m1[c0] ? 4u : 0u;
+        if (c1 < nk64) fl |= m1[c1] ? 8u : 0u;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, fl != 0);
+    if (fl) irow[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<int32_t>(kt | (fl << 28));
+    base += __popc(bal);
+  }
+  for (int j = base + lane; j < nk128; j += 32) irow[j] = -1;
+  if (lane == 0) cnt[tile] = base;
+}
+
 }  // namespace blade
 
 // ================================================================================================
@@ -658,6 +694,18 @@ extern "C" int blade_mask_to_index(const uint8_t* mask, int64_t B, int64_t H, in
   BLADE_REQUIRE(mask && idx && cnt, BLADE_ERR_ARG, "null pointer");
   const int64_t rows = B * H * nq;
   mask_to_index_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, stream>>>(mask, rows, (int)nk, idx, cnt);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+extern "C" int blade_mask64_to_index(const uint8_t* mask, int64_t B, int64_t H, int64_t nq64, int64_t nk64, int32_t* idx,
+                                     int32_t* cnt, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BLADE_REQUIRE(mask && idx && cnt, BLADE_ERR_ARG, "null pointer");
+  const int64_t nq128 = ceil_div(nq64, 2), nk128 = ceil_div(nk64, 2);
+  const int64_t tiles = B * H * nq128;
+  mask64_to_index_kernel<<<static_cast<unsigned>(ceil_div(tiles, 8)), 256, 0, stream>>>(
+      mask, tiles, (int)nq64, (int)nk64, (int)nq128, (int)nk128, idx, cnt);
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
 }
