@@ -74,7 +74,10 @@ typedef struct BladeAsaConfig {
   int32_t num_keep;          /* 32 (W:62) -- sampled estimator only */
   int32_t estimator;         /* 0 = block-mean-pool (north-star kernel (a)), 1 = sampled-max (P) */
   int32_t exact_merge;       /* 1 = reproduce the reference's bf16 op chain W:351-370 (default) */
-  int32_t reserved[7];
+  int32_t rope_first_row;    /* first source row that is rotated (0 wan; text_length cog, MC:59-64) */
+  const float* rope_cos_sin; /* device, fp32 [rows, D/2, 2] (cos, sin) per token and pair, or NULL: rotary embedding
+                                fused into the gather, applied to q and k where the processor does (MW:108-116) */
+  int32_t reserved[4];
 } BladeAsaConfig;
 
 /* ---- introspection -------------------------------------------------------------------------- */
@@ -102,6 +105,14 @@ int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const BladeTensor
                    float* q_mean, float* k_mean,
                    void* k_pool, void* v_pool,
                    int32_t block_size, int32_t sample_gap, void* stream);
+
+/* Same, with the rotary embedding of the processor (MW:108-116 / MC:59-64) applied to q and k on the fly:
+ * rope_cos_sin fp32 [rows, D/2, 2]; source rows < rope_first_row are left alone.  Needs q_r/k_r/v_r. */
+int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                        const int32_t* src_row, void* q_r, void* k_r, void* v_r,
+                        float* q_mean, float* k_mean, void* k_pool, void* v_pool,
+                        int32_t block_size, int32_t sample_gap,
+                        const float* rope_cos_sin, int32_t rope_first_row, void* stream);
 
 /* ---- score estimators: fp32 [B,H,nb,nb] row-normalised block scores -------------------------- */
 int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores,

@@ -392,3 +392,25 @@ def test_block64_layer_config1():
     assert torch.equal(dbg["mask"].cpu(), want_mask)
     ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu())
     _close(out, ref.out)
+
+
+def test_fused_rope_in_prep_matches_reference_rope():
+    """prep with the rotary table == reference apply_rotary_emb (float64 complex, MW:108-116) then gather."""
+    grid = (26, 15, 4)
+    S, H, D = 1560, 2, 128
+    q, k, v = O.synth_qkv(1, H, S, D, seed=23)
+    g = torch.Generator().manual_seed(2)
+    ang = torch.rand(1, 1, S, D // 2, generator=g, dtype=torch.float64) * 6.28
+    freqs = torch.polar(torch.ones_like(ang), ang)
+    table = torch.stack([freqs.real, freqs.imag], -1).reshape(S, D // 2, 2).float().contiguous().cuda()
+    eng = _engine(width=grid[0], height=grid[1], depth=grid[2])
+    (qr, kr, vr), (qm, km), _ = eng.prep(q.cuda(), k.cuda(), v.cuda(), rearrange=True, rope=(table, 0))
+    rr = O.GilbertRearranger(*grid)
+    want_q = rr.rearrange(O.apply_rotary_emb_wan(q, freqs))
+    want_k = rr.rearrange(O.apply_rotary_emb_wan(k, freqs))
+    for got, want in ((qr, want_q), (kr, want_k)):
+        d = (got.float().cpu() - want.float()).abs()
+        assert float(d.max()) <= 2 ** -5                     # <= 1 bf16 ulp at |x| < 8 (fp32 vs fp64 rounding ties)
+        assert float((d > 0).float().mean()) < 0.01
+    assert torch.equal(vr.cpu(), rr.rearrange(v))
+    _close(qm, O.pad_to_multiple(qr.cpu(), 128).float().reshape(1, H, -1, 128, D).mean(3), 1e-5, 1e-5)

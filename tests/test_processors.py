@@ -61,8 +61,12 @@ def test_wan_processor_end_to_end():
         x = torch.randn(1, S, H * D, device="cuda", dtype=torch.bfloat16)
         ang = torch.rand(1, 1, S, D // 2, device="cuda") * 6.28
         freqs = torch.polar(torch.ones_like(ang), ang)
-        out = attn(x, rotary_emb=freqs)
+        out = attn(x, rotary_emb=freqs)                                  # rotary embedding fused into the gather kernel
         assert out.shape == x.shape and out.dtype == x.dtype and torch.isfinite(out.float()).all()
+        attn.set_processor(MW.WanAttnProcessor2_0(fuse_rope=False))     # same thing with the torch rotary path
+        out_t = attn(x, rotary_emb=freqs)
+        dd = out.float() - out_t.float()
+        assert float(dd.norm() / out_t.float().norm()) <= 1e-2, float(dd.norm() / out_t.float().norm())
 
         # same processor, oracle as inner attention (fed the kernel's own fp32 scores)
         captured = {}
@@ -104,5 +108,10 @@ def test_cog_processor_end_to_end():
         hs, ehs = attn(x, encoder_hidden_states=txt, image_rotary_emb=(cos, sin))
         assert hs.shape == x.shape and ehs.shape == txt.shape
         assert torch.isfinite(hs.float()).all() and torch.isfinite(ehs.float()).all()
+        attn.set_processor(MC.SageAttnCogVideoXAttnProcessor(0, fuse_rope=False))
+        hs_t, ehs_t = attn(x, encoder_hidden_states=txt, image_rotary_emb=(cos, sin))
+        for a_, b_ in ((hs, hs_t), (ehs, ehs_t)):
+            dd = a_.float() - b_.float()
+            assert float(dd.norm() / b_.float().norm()) <= 1e-2
     finally:
         C.width, C.height, C.depth, C.text_length, C.max_retain_ratio = 45, 30, 13, 226, 0.1

@@ -24,7 +24,7 @@ class BladeAsaConfig(C.Structure):
     _fields_ = [("block_size", C.c_int32), ("sample_gap", C.c_int32), ("min_retain", C.c_int32),
                 ("max_retain", C.c_int32), ("energy_threshold", C.c_float), ("force_last", C.c_int32),
                 ("num_keep", C.c_int32), ("estimator", C.c_int32), ("exact_merge", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("rope_first_row", C.c_int32), ("rope_cos_sin", C.c_void_p), ("reserved", C.c_int32 * 4)]
 
 
 # every symbol include/blade_asa.h declares (tests/test_cabi_symbols.py checks the list against the header)
@@ -33,7 +33,7 @@ SYMBOLS = [
     "blade_asa_workspace_bytes", "blade_asa_prep", "blade_asa_scores_meanpool", "blade_asa_select",
     "blade_mask_to_index", "blade_block_sparse_attn_fwd", "blade_asa_attn_fwd", "blade_asa_forward",
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
-    "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd",
+    "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -58,6 +58,7 @@ def load() -> C.CDLL:
     lib.blade_asa_workspace_bytes.argtypes = [i64, i64, i64, i64, CFG]
     lib.blade_asa_workspace_bytes.restype = C.c_size_t
     lib.blade_asa_prep.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.blade_asa_prep_rope.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp]
     lib.blade_asa_scores_meanpool.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
     lib.blade_asa_select.argtypes = [vp, i64, i64, i64, i64, CFG, vp, vp, vp, vp, vp, vp, vp]
     lib.blade_mask_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
@@ -72,8 +73,6 @@ def load() -> C.CDLL:
     lib.blade_asa_attn64_fwd.argtypes = lib.blade_asa_attn_fwd.argtypes
     lib.blade_asa_sample_tokens.argtypes = [T, T, vp, vp, vp, vp, i32, vp]
     lib.blade_asa_scores_sampled.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, vp]
-    if hasattr(lib, "blade_rope_pack"):
-        lib.blade_rope_pack.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("blade_abi_version",):

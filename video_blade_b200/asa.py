@@ -168,8 +168,9 @@ class AsaEngine:
                                            current_stream()))
         return idx, cnt
 
-    def prep(self, q, k, v, rearrange: bool, want_means=True, want_pool=True):
-        """Gather into Gilbert order (optional) + block means + gap-pooled K/V."""
+    def prep(self, q, k, v, rearrange: bool, want_means=True, want_pool=True, rope=None):
+        """Gather into Gilbert order (optional) + block means + gap-pooled K/V.  rope = (table fp32 [rows,D/2,2],
+        first_row): rotary embedding of q and k fused into the gather (needs the output copies)."""
         self._require_cuda(q, k, v)
         B, H, S, D = q.shape
         kn = self.knobs
@@ -177,7 +178,7 @@ class AsaEngine:
         src = self.src_row(dev, S) if rearrange else None
         nb = -(-S // kn.block_size)
         q_r = k_r = v_r = None
-        if src is not None:
+        if src is not None or rope is not None:
             q_r = torch.empty(B, H, S, D, dtype=q.dtype, device=dev)
             k_r = torch.empty_like(q_r)
             v_r = torch.empty_like(q_r)
@@ -190,9 +191,10 @@ class AsaEngine:
             npool = -(-S // gap)
             kp = torch.empty(B, H, npool, D, dtype=q.dtype, device=dev)
             vp = torch.empty_like(kp)
-        check(self.lib.blade_asa_prep(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)),
-                                      ptr(src), ptr(q_r), ptr(k_r), ptr(v_r), ptr(qm), ptr(km), ptr(kp), ptr(vp),
-                                      kn.block_size, gap, current_stream()))
+        table, first = rope if rope is not None else (None, 0)
+        check(self.lib.blade_asa_prep_rope(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)),
+                                           ptr(src), ptr(q_r), ptr(k_r), ptr(v_r), ptr(qm), ptr(km), ptr(kp), ptr(vp),
+                                           kn.block_size, gap, ptr(table), int(first), current_stream()))
         return (q_r, k_r, v_r), (qm, km), (kp, vp)
 
     def scores_meanpool(self, qm: torch.Tensor, km: torch.Tensor) -> torch.Tensor:
@@ -228,15 +230,16 @@ class AsaEngine:
                                                 _lib._dtype_code(q), current_stream()))
         return sc
 
-    def _forward_staged(self, q, k, v, q_off, k_off, return_debug, scores=None):
+    def _forward_staged(self, q, k, v, q_off, k_off, return_debug, scores=None, rope=None):
         """The layer as separate C-ABI calls (prep, score, select, attention): used for estimator ==
         "sampled_max" and for block_size 64 (blade_asa_forward covers the default block-128 mean-pool path)."""
         B, H, S, D = q.shape
         kn = self.knobs
         rearr = kn.use_rearrange
         sampled = kn.estimator == "sampled_max" and scores is None
-        (qr, kr, vr), (qm, km), (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=not sampled and scores is None)
-        if not rearr:
+        (qr, kr, vr), (qm, km), (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=not sampled and scores is None,
+                                                     rope=rope)
+        if qr is None:
             qr, kr, vr = q, k, v
         if scores is not None:
             sc = scores
@@ -311,7 +314,7 @@ class AsaEngine:
 
     # ---- the whole layer ------------------------------------------------------------------
     def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
-                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None):
+                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None):
         """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
         token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
         processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous."""
@@ -323,9 +326,16 @@ class AsaEngine:
             if virtual_rows is not None:
                 raise ValueError("staged path (sampled_max / block 64): the packed Ulysses receive layout is not wired yet")
             qo, ko = sample_offsets if sample_offsets is not None else (None, None)
-            return self._forward_staged(q, k, v, qo, ko, return_debug, scores=scores)
+            return self._forward_staged(q, k, v, qo, ko, return_debug, scores=scores, rope=rope)
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
+        if rope is not None:
+            if virtual_rows is not None:
+                raise ValueError("fused rotary embedding: not available on the packed Ulysses receive layout")
+            table, first = rope
+            assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[-2:] == (D // 2, 2)
+            cfg.rope_cos_sin = table.data_ptr()
+            cfg.rope_first_row = int(first)
         src = self.src_row(dev, S)
         dst = src
         if virtual_rows is not None:

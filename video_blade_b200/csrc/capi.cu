@@ -189,7 +189,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const int64_t nb = ceil_div(S, cfg->block_size);
   const int64_t np = cfg->sample_gap > 0 ? ceil_div(S, cfg->sample_gap) : 0;
-  const bool rearr = src_row != nullptr;
+  const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr;  // rotation needs the output copies too
   float* q_mean = reinterpret_cast<float*>(ws + w.q_mean);
   float* k_mean = reinterpret_cast<float*>(ws + w.k_mean);
   float* scores = scores_out ? scores_out : reinterpret_cast<float*>(ws + w.scores);
@@ -197,10 +197,11 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   int32_t* cnt = cnt_out ? cnt_out : reinterpret_cast<int32_t*>(ws + w.cnt);
 
   const bool need_means = scores_in == nullptr;
-  if (int e = blade_asa_prep(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
-                             rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr,
-                             need_means ? k_mean : nullptr, np ? ws + w.k_pool : nullptr,
-                             np ? ws + w.v_pool : nullptr, cfg->block_size, cfg->sample_gap, stream))
+  if (int e = blade_asa_prep_rope(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
+                                  rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr,
+                                  need_means ? k_mean : nullptr, np ? ws + w.k_pool : nullptr,
+                                  np ? ws + w.v_pool : nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin,
+                                  cfg->rope_first_row, stream))
     return e;
   const float* sc = scores_in;
   if (!sc) {

@@ -65,13 +65,14 @@ struct Strides3 {
 // ------------------------------------------------------------------------------------------------
 // prep: grid (nb, H, B), 256 threads.  One CTA = one block of `block` output rows of one head.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool IS_BF16, bool COPY>
+template <int D, bool IS_BF16, bool COPY, bool ROPE>
 __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
                                                          const uint16_t* __restrict__ v, Strides3 sq, Strides3 sk,
                                                          Strides3 sv, const int32_t* __restrict__ src_row,
                                                          uint16_t* __restrict__ q_r, uint16_t* __restrict__ k_r,
                                                          uint16_t* __restrict__ v_r, float* __restrict__ q_mean,
-                                                         float* __restrict__ k_mean, int S, int H, int nb, int block) {
+                                                         float* __restrict__ k_mean, int S, int H, int nb, int block,
+                                                         const float* __restrict__ rope, int rope_first) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
     for (int p0 = 0; p0 < passes; p0 += 8) {
       uint4 val[8];
       int rows[8];
+      int srcs[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int p = p0 + u;
@@ -109,7 +111,28 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
         rows[u] = r;
         const int rc = r < S ? r : S - 1;  // replicate padding (W:35)
         const int sr = src_row ? __ldg(src_row + rc) : rc;
+        srcs[u] = sr;
         if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
+      }
+      if (ROPE && t < 2) {
+        // rotary embedding where the reference applies it (modify_wan.py:108-116 / modify_cogvideo.py:59-64):
+        // pairs (x[2i], x[2i+1]) times (cos, sin) of the token's position, fp32, rounded back to the tensor dtype
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (p0 + u >= passes || srcs[u] < rope_first) continue;
+          const float4* tp = reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(srcs[u] - rope_first) * (D / 2) + chunk * 4) * 2);
+          const float4 c01 = __ldg(tp), c23 = __ldg(tp + 1);  // (cos0,sin0,cos1,sin1), (cos2,sin2,cos3,sin3)
+          float f[8];
+          unpack8<IS_BF16>(val[u], f);
+          const float cs[8] = {c01.x, c01.y, c01.z, c01.w, c23.x, c23.y, c23.z, c23.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = f[2 * i], bb = f[2 * i + 1];
+            f[2 * i] = a * cs[2 * i] - bb * cs[2 * i + 1];
+            f[2 * i + 1] = a * cs[2 * i + 1] + bb * cs[2 * i];
+          }
+          val[u] = pack8<IS_BF16>(f);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -578,6 +601,14 @@ using namespace blade;
 extern "C" int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row,
                               void* q_r, void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool,
                               void* v_pool, int32_t block_size, int32_t sample_gap, void* stream_) {
+  return blade_asa_prep_rope(q, k, v, src_row, q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, block_size, sample_gap,
+                             nullptr, 0, stream_);
+}
+
+extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                                   const int32_t* src_row, void* q_r, void* k_r, void* v_r, float* q_mean,
+                                   float* k_mean, void* k_pool, void* v_pool, int32_t block_size, int32_t sample_gap,
+                                   const float* rope_cos_sin, int32_t rope_first_row, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
@@ -592,6 +623,9 @@ extern "C" int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const 
   const bool copy = q_r || k_r || v_r;
   BLADE_REQUIRE(!copy || (q_r && k_r && v_r), BLADE_ERR_ARG, "q_r/k_r/v_r must be all set or all NULL");
   BLADE_REQUIRE(copy || !src_row, BLADE_ERR_ARG, "src_row given but no output copies requested");
+  BLADE_REQUIRE(copy || !rope_cos_sin, BLADE_ERR_ARG, "rotary embedding needs the q_r/k_r/v_r outputs");
+  BLADE_REQUIRE(!rope_cos_sin || (reinterpret_cast<uintptr_t>(rope_cos_sin) & 15) == 0, BLADE_ERR_ALIGN,
+                "rope table not 16B aligned");
   const int nb = static_cast<int>(ceil_div(S, block_size));
   const bool bf = q->dtype == BLADE_BF16;
   Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
@@ -601,18 +635,24 @@ extern "C" int blade_asa_prep(const BladeTensor* q, const BladeTensor* k, const 
                  *vp = static_cast<const uint16_t*>(v->ptr);
   if (q_mean || k_mean || copy) {
     dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
-#define LAUNCH_PREP(DD, BF, CP)                                                                                   \
-  prep_block_kernel<DD, BF, CP><<<grid, 256, 0, stream>>>(qp, kp, vp, sq, sk, sv, src_row,                        \
-                                                          static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
-                                                          static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
-                                                          static_cast<int>(S), static_cast<int>(H), nb, block_size)
-    if (D == 128) {
-      if (bf) { if (copy) LAUNCH_PREP(128, true, true); else LAUNCH_PREP(128, true, false); }
-      else    { if (copy) LAUNCH_PREP(128, false, true); else LAUNCH_PREP(128, false, false); }
-    } else {
-      if (bf) { if (copy) LAUNCH_PREP(64, true, true); else LAUNCH_PREP(64, true, false); }
-      else    { if (copy) LAUNCH_PREP(64, false, true); else LAUNCH_PREP(64, false, false); }
-    }
+#define LAUNCH_PREP(DD, BF, CP, RP)                                                                               \
+  prep_block_kernel<DD, BF, CP, RP><<<grid, 256, 0, stream>>>(qp, kp, vp, sq, sk, sv, src_row,                        \
+                                                              static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
+                                                              static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
+                                                              static_cast<int>(S), static_cast<int>(H), nb, block_size, \
+                                                              rope_cos_sin, rope_first_row)
+#define LAUNCH_PREP_D(DD)                                                                                             \
+  do {                                                                                                                \
+    if (rope_cos_sin) {                                                                                               \
+      if (bf) LAUNCH_PREP(DD, true, true, true); else LAUNCH_PREP(DD, false, true, true);                             \
+    } else if (copy) {                                                                                                \
+      if (bf) LAUNCH_PREP(DD, true, true, false); else LAUNCH_PREP(DD, false, true, false);                           \
+    } else {                                                                                                          \
+      if (bf) LAUNCH_PREP(DD, true, false, false); else LAUNCH_PREP(DD, false, false, false);                         \
+    }                                                                                                                 \
+  } while (0)
+    if (D == 128) LAUNCH_PREP_D(128); else LAUNCH_PREP_D(64);
+#undef LAUNCH_PREP_D
 #undef LAUNCH_PREP
     BLADE_CUDA_OK(cudaGetLastError());
   }

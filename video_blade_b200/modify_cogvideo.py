@@ -26,8 +26,10 @@ def apply_rotary_emb(x: torch.Tensor, freqs_cis) -> torch.Tensor:
 class SageAttnCogVideoXAttnProcessor:
     """MC:11-76."""
 
-    def __init__(self, idx):
+    def __init__(self, idx, fuse_rope: bool = True):
         self.idx = idx
+        self.fuse_rope = fuse_rope
+        self._table = None
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor,
                  attention_mask: Optional[torch.Tensor] = None, image_rotary_emb=None):
@@ -48,11 +50,24 @@ class SageAttnCogVideoXAttnProcessor:
             query = attn.norm_q(query).to(dtype=value.dtype)
         if attn.norm_k is not None:
             key = attn.norm_k(key).to(dtype=value.dtype)
+        fused_rope = None
         if image_rotary_emb is not None:                                       # MC:59-64
-            query[:, :, text_seq_length:] = apply_rotary_emb(query[:, :, text_seq_length:], image_rotary_emb)
-            if not attn.is_cross_attention:
-                key[:, :, text_seq_length:] = apply_rotary_emb(key[:, :, text_seq_length:], image_rotary_emb)
-        hidden_states = attn.inner_attention(query, key, value)                # MC:65 (no .contiguous() needed)
+            if getattr(attn.inner_attention, "supports_fused_rope", False) and not attn.is_cross_attention \
+                    and query.is_cuda and self.fuse_rope:
+                cos, sin = image_rotary_emb                                    # [Sv, D], repeat-interleaved pairs
+                key_ = (cos.data_ptr(), sin.data_ptr())
+                if self._table is None or self._table[0] != key_:
+                    tab = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(query.device, torch.float32).contiguous()
+                    self._table = (key_, tab)
+                fused_rope = (self._table[1], text_seq_length)                 # video rows only
+            else:
+                query[:, :, text_seq_length:] = apply_rotary_emb(query[:, :, text_seq_length:], image_rotary_emb)
+                if not attn.is_cross_attention:
+                    key[:, :, text_seq_length:] = apply_rotary_emb(key[:, :, text_seq_length:], image_rotary_emb)
+        if fused_rope is not None:
+            hidden_states = attn.inner_attention(query, key, value, rotary=fused_rope)
+        else:
+            hidden_states = attn.inner_attention(query, key, value)            # MC:65 (no .contiguous() needed)
         hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim)
         hidden_states = attn.to_out[0](hidden_states)
         hidden_states = attn.to_out[1](hidden_states)

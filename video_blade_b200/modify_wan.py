@@ -25,11 +25,27 @@ def apply_rotary_emb(hidden_states: torch.Tensor, freqs: torch.Tensor) -> torch.
     return torch.view_as_real(x * f).flatten(3, 4).type_as(hidden_states)
 
 
+_ROPE_TABLES = {}
+
+
+def _rope_table(freqs: torch.Tensor) -> torch.Tensor:
+    """complex rotary table [1,1,S,D/2] -> fp32 [S, D/2, 2] of (cos, sin), cached per tensor."""
+    key = (freqs.data_ptr(), tuple(freqs.shape), str(freqs.device))
+    t = _ROPE_TABLES.get(key)
+    if t is None:
+        f = freqs.reshape(freqs.shape[-2], freqs.shape[-1])
+        t = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous()
+        if len(_ROPE_TABLES) > 16:
+            _ROPE_TABLES.clear()
+        _ROPE_TABLES[key] = t
+    return t
+
+
 class WanAttnProcessor2_0:
     """MW:75-148."""
 
-    def __init__(self):
-        pass
+    def __init__(self, fuse_rope: bool = True):
+        self.fuse_rope = fuse_rope
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -50,9 +66,14 @@ class WanAttnProcessor2_0:
         query = query.unflatten(2, (attn.heads, -1)).transpose(1, 2)           # MW:104-106: strided views
         key = key.unflatten(2, (attn.heads, -1)).transpose(1, 2)
         value = value.unflatten(2, (attn.heads, -1)).transpose(1, 2)
+        fused_rope = None
         if rotary_emb is not None:                                             # MW:108-116
-            query = apply_rotary_emb(query, rotary_emb)
-            key = apply_rotary_emb(key, rotary_emb)
+            if getattr(attn.inner_attention, "supports_fused_rope", False) and getattr(attn, "add_k_proj", None) is None \
+                    and query.is_cuda and self.fuse_rope:
+                fused_rope = (_rope_table(rotary_emb), 0)                      # rotated inside the gather kernel
+            else:
+                query = apply_rotary_emb(query, rotary_emb)
+                key = apply_rotary_emb(key, rotary_emb)
 
         hidden_states_img = None
         if encoder_hidden_states_img is not None:                              # MW:118-131
@@ -63,7 +84,10 @@ class WanAttnProcessor2_0:
             hidden_states_img = attn.inner_attention(query, key_img, value_img)
             hidden_states_img = hidden_states_img.transpose(1, 2).flatten(2, 3).type_as(query)
 
-        hidden_states = attn.inner_attention(query, key, value)                # MW:135
+        if fused_rope is not None:
+            hidden_states = attn.inner_attention(query, key, value, rotary=fused_rope)
+        else:
+            hidden_states = attn.inner_attention(query, key, value)            # MW:135
         hidden_states = hidden_states.transpose(1, 2).flatten(2, 3)            # a view: output memory is [B,S,H,D]
         hidden_states = hidden_states.type_as(query)
         if hidden_states_img is not None:
