@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -101,6 +101,15 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def traffic_bytes():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["asa_attn_kernel<128,bf16>"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def make_inputs(B, H, S, D, kind, seed, grid):
@@ -263,7 +272,6 @@ def run_blade(args):
     per_step = timed(args.steps, lambda: layer(dq, dk, dv), with_stage_events=True)
     barrier()
     wall = time.perf_counter() - wall0
-    clk = clocks.stop() if rank == 0 else None
     dev_ms = sum(per_step)
     stage_ms = [sum(ev[i][s][0].elapsed_time(ev[i][s][1]) for i in range(args.steps)) / args.steps for s in range(4)]
 
@@ -312,6 +320,7 @@ def run_blade(args):
     e2e_ms = e2e_run(args.steps)
     barrier()
     out_host = ohost[0]
+    clk = clocks.stop() if rank == 0 else None      # sampled over the timed layer loop and the e2e loop
 
     # ---- Ulysses configuration (config 3 topology): B = 2 as 2 CFG groups x Ulysses N/2
     ulysses = None
@@ -380,8 +389,9 @@ def run_blade(args):
             "roofline": {"kernel": "asa_attn_kernel<128,bf16>", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
                          "frac_of_sustained": achieved / peaks["tf_sustained"] if peaks["tf_sustained"] else None,
-                         "peak_source": peaks["source"], "avg_launch_ms": attn_ms, "traffic": None},
-            "roofline_maskgen": {"kernel": "prep_block_kernel + pool_kernel", "bound": "hbm",
+                         "peak_source": peaks["source"], "avg_launch_ms": attn_ms, "traffic": traffic_bytes(),
+                         "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic.json)"},
+            "roofline_maskgen": {"kernel": "prep_block_kernel (gather + copy + block means)", "bound": "hbm",
                                  "achieved": (2 * 3 * Hl * S * D * 2) / (stage_ms[0] * 1e-3) / 1e9,
                                  "peak": peaks["hbm"], "unit": "GB/s", "avg_ms": stage_ms[0]},
             "clocks": clk, "wall_s_timed_region": wall,

@@ -442,13 +442,15 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               ls[i & 3] += p0 + p1;
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }
-            tmem_st16(tS + c * 16, pk);
-            if (c == 1) {  // first 64 keys of P are complete: let the tensor core start on them
+            if (c == 2) {
+              // split-P: keys 0..63 of P (chunks 0,1) were stored a chunk of exponentials ago, so this wait is
+              // free; the tensor core starts PV on them while chunks 2,3 are still being produced
               tmem_wait_st();
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&mz->p_lo[t]);
             }
+            tmem_st16(tS + c * 16, pk);
           }
           l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
           if (wq == 0) TRACE(t, 3, g);

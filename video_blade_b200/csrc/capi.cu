@@ -95,6 +95,24 @@ static void gilbert_fill(int W, int H, int D, int64_t* curve2raster) {
   }
 }
 
+// side stream + events for the fork/join inside blade_asa_forward (created once per process and device)
+struct ForkState {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ForkState* fork_state() {
+  static ForkState st[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ForkState* f = &st[dev & 15];
+  if (!f->side) {
+    cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming);
+  }
+  return f;
+}
+
 // workspace carving for blade_asa_forward
 struct ForwardWs {
   size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, total;
@@ -197,12 +215,24 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   int32_t* cnt = cnt_out ? cnt_out : reinterpret_cast<int32_t*>(ws + w.cnt);
 
   const bool need_means = scores_in == nullptr;
-  if (int e = blade_asa_prep_rope(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
-                                  rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr,
-                                  need_means ? k_mean : nullptr, np ? ws + w.k_pool : nullptr,
-                                  np ? ws + w.v_pool : nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin,
-                                  cfg->rope_first_row, stream))
+  // gather / rotate / block means on the caller's stream ...
+  if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
+                        rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
+                        nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
+                        stream))
     return e;
+  // ... then the bandwidth-bound gap pooling forks onto a side stream and overlaps the latency-bound score and
+  // selection kernels; it is joined again right before the attention launch (events only, no host sync).
+  ForkState* fk = np ? fork_state() : nullptr;
+  if (np) {
+    BLADE_CUDA_OK(cudaEventRecord(fk->fork, stream));
+    BLADE_CUDA_OK(cudaStreamWaitEvent(fk->side, fk->fork, 0));
+    if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
+                          rearr ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool,
+                          cfg->block_size, cfg->sample_gap, nullptr, 0, 2, fk->side))
+      return e;
+    BLADE_CUDA_OK(cudaEventRecord(fk->join, fk->side));
+  }
   const float* sc = scores_in;
   if (!sc) {
     if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, stream)) return e;
@@ -212,6 +242,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   }
   if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, stream)) return e;
 
+  if (np) BLADE_CUDA_OK(cudaStreamWaitEvent(stream, fk->join, 0));
   BladeTensor qr = *q, kr = *k, vr = *v;
   if (rearr) {
     const int64_t cs[4] = {H * S * D, S * D, D, 1};

@@ -41,12 +41,16 @@ struct StageTimer {
   int stage;
   cudaStream_t stream;
   StageTimer(int s, cudaStream_t st) : stage(s), stream(st) {
-    if (stage_events()[stage].start) cudaEventRecord(stage_events()[stage].start, stream);
+    if (stage >= 0 && stage_events()[stage].start) cudaEventRecord(stage_events()[stage].start, stream);
   }
   ~StageTimer() {
-    if (stage_events()[stage].stop) cudaEventRecord(stage_events()[stage].stop, stream);
+    if (stage >= 0 && stage_events()[stage].stop) cudaEventRecord(stage_events()[stage].stop, stream);
   }
 };
+
+int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
+              void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
+              int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

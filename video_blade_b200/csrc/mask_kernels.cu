@@ -609,7 +609,15 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
                                    const int32_t* src_row, void* q_r, void* k_r, void* v_r, float* q_mean,
                                    float* k_mean, void* k_pool, void* v_pool, int32_t block_size, int32_t sample_gap,
                                    const float* rope_cos_sin, int32_t rope_first_row, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return blade::prep_impl(q, k, v, src_row, q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, block_size, sample_gap,
+                          rope_cos_sin, rope_first_row, 3, static_cast<cudaStream_t>(stream_));
+}
+
+// parts: bit 0 = gather/copy/means kernel, bit 1 = gap-pooling kernel (reads the copies when they exist)
+int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
+                     void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool,
+                     int32_t block_size, int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row,
+                     int parts, cudaStream_t stream) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -630,10 +638,10 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
   const bool bf = q->dtype == BLADE_BF16;
   Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
       sv{v->stride[0], v->stride[1], v->stride[2]};
-  StageTimer timer(0, stream);
+  StageTimer timer(parts == 2 ? -1 : 0, stream);
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
-  if (q_mean || k_mean || copy) {
+  if ((parts & 1) && (q_mean || k_mean || copy)) {
     dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
 #define LAUNCH_PREP(DD, BF, CP, RP)                                                                               \
   prep_block_kernel<DD, BF, CP, RP><<<grid, 256, 0, stream>>>(qp, kp, vp, sq, sk, sv, src_row,                        \
@@ -656,7 +664,7 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
 #undef LAUNCH_PREP
     BLADE_CUDA_OK(cudaGetLastError());
   }
-  if (sample_gap > 0 && k_pool && v_pool) {
+  if ((parts & 2) && sample_gap > 0 && k_pool && v_pool) {
     const int np = static_cast<int>(ceil_div(S, sample_gap));
     // read the curve-ordered copies when they exist (contiguous, no gather), else the sources
     const uint16_t* ks = copy ? static_cast<const uint16_t*>(k_r) : kp;
