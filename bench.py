@@ -40,6 +40,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "Wan2.1-T2V-1.3B ASA layer 81x480x832 (32760 tok, 12 heads, d=128), block 128, retain 0.05-0.17, gap 30"
+WORKLOAD_COG = ("CogVideoX-5B ASA layer 49x480x720 (17550 video + 226 text tok, 48 heads, d=64), block 128, "
+                "retain 0.05-0.10, gap 15, last two block rows/cols dense")
+
+
+def workload(args):
+    """(knobs, H, D, name) of the requested BASELINE config: wan = config 2 (default), cog = config 4."""
+    from video_blade_b200.asa import AsaKnobs
+    if args.workload == "cog":
+        kn, H, D, name = AsaKnobs.cog(), 48, 64, WORKLOAD_COG
+    else:
+        kn, H, D, name = AsaKnobs.wan(), 12, 128, WORKLOAD
+    if args.retain is not None:                      # config 5 sweep: pin the density with min = max
+        kn.max_retain_ratio = kn.min_retain_ratio = args.retain
+        name += f", min=max retain {args.retain}"
+    return kn, H, D, name
 
 
 # --------------------------------------------------------------------------------------------- helpers
@@ -112,9 +127,10 @@ def traffic_bytes():
         return None
 
 
-def make_inputs(B, H, S, D, kind, seed, grid):
+def make_inputs(B, H, S, D, kind, seed, grid, text_length=0):
     from oracle.asa_oracle import synth_qkv     # synthetic-input recipe shared with the tests (not timed)
-    q, k, v = synth_qkv(B, H, S, D, seed=seed, structured=2.0 if kind == "structured" else 0.0, grid=grid)
+    q, k, v = synth_qkv(B, H, S, D, seed=seed, structured=2.0 if kind == "structured" else 0.0, grid=grid,
+                        text_length=text_length)
     # the reference hands the module transposed views of [B,S,H,D] memory (modify_wan.py:104-106)
     return tuple(x.transpose(1, 2).contiguous() for x in (q, k, v))     # [B,S,H,D] host tensors
 
@@ -136,9 +152,9 @@ def cpu_reference_sample(q, k, v, kn, heads=1, threads=None):
     from oracle import asa_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    cfg = O.ASAConfig.wan(width=kn.width, height=kn.height, depth=kn.depth, sample_gap=kn.sample_gap,
-                          max_retain_ratio=kn.max_retain_ratio, min_retain_ratio=kn.min_retain_ratio,
-                          estimator="meanpool")
+    cfg = O.ASAConfig(flavor=kn.flavor, width=kn.width, height=kn.height, depth=kn.depth, sample_gap=kn.sample_gap,
+                      text_length=kn.text_length, max_retain_ratio=kn.max_retain_ratio,
+                      min_retain_ratio=kn.min_retain_ratio, estimator="meanpool")
     qs, ks, vs = (x[:, :, :heads].transpose(1, 2) for x in (q, k, v))          # [B,heads,S,D] views
     rr = O.GilbertRearranger(cfg.width, cfg.height, cfg.depth, cfg.text_length)
     t0 = time.perf_counter()
@@ -156,9 +172,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kn = AsaKnobs.wan()
-    S, H, D = kn.width * kn.height * kn.depth, 12, 128
-    q, k, v = make_inputs(1, H, S, D, args.inputs, 0, (kn.width, kn.height, kn.depth))
+    kn, H, D, wname = workload(args)
+    S = kn.width * kn.height * kn.depth + kn.text_length
+    q, k, v = make_inputs(1, H, S, D, args.inputs, 0, (kn.width, kn.height, kn.depth), kn.text_length)
     heads = 1
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
@@ -170,12 +186,12 @@ def run_reference(args):
         ts.append(dt)
     t = sum(ts) / len(ts)
     val = fl / t / 1e12
-    sample = f"{heads} of {H} heads of the workload (all 32760 query rows, dense-masked fp32 + pooled branch + merge)"
+    sample = f"{heads} of {H} heads of the workload (all {S} query rows, dense-masked fp32 + pooled branch + merge)"
     line = {"metric": "ASA sparse-effective attention throughput (whole layer)", "value": val, "unit": "TFLOP/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": t * 1e3, "ms_per_layer_extrapolated": t * 1e3 * H / heads,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 in / fp32 math",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "inputs": args.inputs},
+            "data": "synthetic", "config": {"workload": wname, "inputs": args.inputs},
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -199,8 +215,8 @@ def run_blade(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    kn = AsaKnobs.wan()
-    S, H, D = kn.width * kn.height * kn.depth, 12, 128
+    kn, H, D, wname = workload(args)
+    S = kn.width * kn.height * kn.depth + kn.text_length
     n_pool = -(-S // kn.sample_gap)
     eng = AsaEngine(kn)
     peaks = load_peaks()
@@ -211,8 +227,8 @@ def run_blade(args):
     ug = None
     Hl = H
 
-    q, k, v = make_inputs(1, H, S, D, args.inputs, group_id, (kn.width, kn.height, kn.depth))   # host [1,S,H,D]
-    hq, hk, hv = (x.pin_memory() for x in (q, k, v))
+    q, k, v = make_inputs(1, H, S, D, args.inputs, group_id, (kn.width, kn.height, kn.depth), kn.text_length)
+    hq, hk, hv = (x.pin_memory() for x in (q, k, v))                                           # host [1,S,H,D]
     dq, dk, dv = (x.to(dev) for x in (hq, hk, hv))
     out_host = torch.empty(dq.shape, dtype=dq.dtype).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
@@ -328,7 +344,7 @@ def run_blade(args):
         Pu = world // 2
         ugrp = UlyssesGroup(world, rank, Pu)
         gid, pr = rank // Pu, rank % Pu
-        uq, uk, uv = make_inputs(1, H, S, D, args.inputs, gid, (kn.width, kn.height, kn.depth))
+        uq, uk, uv = make_inputs(1, H, S, D, args.inputs, gid, (kn.width, kn.height, kn.depth), kn.text_length)
         sl = slice(pr * (S // Pu), (pr + 1) * (S // Pu))
         uq, uk, uv = (x[:, sl].contiguous().to(dev) for x in (uq, uk, uv))                    # my sequence shard
 
@@ -377,7 +393,7 @@ def run_blade(args):
             "ms_per_layer": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "inputs": args.inputs, "global_batch": B_glob,
+            "config": {"workload": wname, "inputs": args.inputs, "global_batch": B_glob,
                        "parallelism": "single" if world == 1 else f"batch{world} (CFG/prompt split, no data-path collective)",
                        "l2": "256 MiB flush between timed iterations", "retained_blocks_per_row_mean": retained_mean,
                        "algorithmic_tflop_per_step": total_flops / 1e12,
@@ -386,10 +402,11 @@ def run_blade(args):
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 3 * hq.numel() * 2 * world, "d2h_bytes_per_step": out_host.numel() * 2 * world},
             "gpu_launches": args.steps * 5,
-            "roofline": {"kernel": "asa_attn_kernel<128,bf16>", "bound": "tensor", "achieved": achieved,
+            "roofline": {"kernel": f"asa_attn_kernel<{D},bf16>", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
                          "frac_of_sustained": achieved / peaks["tf_sustained"] if peaks["tf_sustained"] else None,
-                         "peak_source": peaks["source"], "avg_launch_ms": attn_ms, "traffic": traffic_bytes(),
+                         "peak_source": peaks["source"], "avg_launch_ms": attn_ms,
+                         "traffic": traffic_bytes() if args.workload == "wan" and args.retain is None else None,
                          "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic.json)"},
             "roofline_maskgen": {"kernel": "prep_block_kernel (gather + copy + block means)", "bound": "hbm",
                                  "achieved": (2 * 3 * Hl * S * D * 2) / (stage_ms[0] * 1e-3) / 1e9,
@@ -403,7 +420,7 @@ def run_blade(args):
             dt, fl, thr = cpu_reference_sample(q, k, v, kn, heads=1)
             line["cpu_baseline"] = {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": thr, "kind": "port",
                                     "seconds": dt,
-                                    "sample": "1 of 12 heads of the workload (all 32760 query rows, dense-masked "
+                                    "sample": f"1 of {H} heads of the workload (all {S} query rows, dense-masked "
                                               "fp32 + pooled branch + merge), one pass"}
         print(json.dumps(line))
     if world > 1:
@@ -418,6 +435,9 @@ def main():
     ap.add_argument("--impl", default="blade", choices=["blade", "reference"])
     ap.add_argument("--inputs", default="gaussian", choices=["gaussian", "structured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="wan", choices=["wan", "cog"],
+                    help="wan = BASELINE config 2 (default, the headline); cog = config 4")
+    ap.add_argument("--retain", type=float, default=None, help="config 5 density sweep: min = max retain ratio")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "blade" else args.warmup
     if args.impl == "reference":
