@@ -414,3 +414,37 @@ def test_fused_rope_in_prep_matches_reference_rope():
         assert float((d > 0).float().mean()) < 0.01
     assert torch.equal(vr.cpu(), rr.rearrange(v))
     _close(qm, O.pad_to_multiple(qr.cpu(), 128).float().reshape(1, H, -1, 128, D).mean(3), 1e-5, 1e-5)
+
+
+# ------------------------------------------------------------------ fp16 (the upstream kernel accepts it too)
+def test_fp16_attention_and_layer():
+    S, H, D = 1560, 2, 128
+    grid = (26, 15, 4)
+    q, k, v = O.synth_qkv(1, H, S, D, seed=31, dtype=torch.float16, structured=2.0, grid=grid)
+    eng = _engine(width=grid[0], height=grid[1], depth=grid[2], max_retain_ratio=0.4)
+    nb = -(-S // 128)
+    mask = _rand_mask(1, H, nb, nb, 0.4, seed=5)
+    idx, cnt = O.mask_to_index_list(mask)
+    eng_nr = _engine(use_rearrange=False)
+    out, lse = eng_nr.block_sparse_attn(q.cuda(), k.cuda(), v.cuda(), idx.cuda(), cnt.cuda())
+    wout, wlse = O.dense_masked_attention(q, k, v, mask)
+    assert out.dtype == torch.float16
+    _close(out, wout, 2e-3, 4e-3)                      # fp16 carries 3 more mantissa bits than bf16
+    _close(lse, wlse, 1e-5, 1e-4)
+    out2, dbg = eng.forward(q.cuda(), k.cuda(), v.cuda(), return_debug=True)
+    cfg = O.ASAConfig.wan(width=grid[0], height=grid[1], depth=grid[2], max_retain_ratio=0.4)
+    ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu())
+    assert torch.equal(dbg["mask"].cpu(), ref.mask)
+    _close(out2, ref.out, 2e-3, 4e-3)
+
+
+def test_select_long_rows_fallback():
+    """nk > 256 takes the rank-counting kernel; same bit-exact contract."""
+    eng = _engine()
+    g = torch.Generator().manual_seed(9)
+    sc = torch.softmax(torch.randn(1, 1, 40, 300, generator=g) * 3.0, -1)
+    want, _ = O.select_blocks_energy(sc, 15, 51, 0.95)
+    idx, cnt, mask = eng.select(sc.cuda(), lo=15, hi=51, force_last=0)
+    assert torch.equal(mask.cpu(), want)
+    widx, wcnt = O.mask_to_index_list(want)
+    assert torch.equal(idx.cpu(), widx) and torch.equal(cnt.cpu(), wcnt)

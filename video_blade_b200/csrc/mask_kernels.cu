@@ -6,10 +6,12 @@
 //                       row, 8 independent loads in flight per thread.
 //   pool_kernel         gap-means of K and V for the global branch (simple_pooling, W:88-93).
 //   score_meanpool_kernel  coarse nb x nb block-score GEMM on the means + row softmax (fp32).
-//   select_kernel       energy-threshold block selection (transfer_attn_to_mask, W:214-229 / C:228-248):
-//                       one warp per score row; stable descending order by rank counting, fp64 sequential
-//                       prefix sums rounded to fp32 (== torch CPU sort(stable)+cumsum, bit-exact),
-//                       ballot compaction into the ascending per-row block-index list.
+//   select_bitonic_kernel / select_rank_kernel
+//                       energy-threshold block selection (transfer_attn_to_mask, W:214-229 / C:228-248):
+//                       one warp per score row; total order (value desc, index asc) by a register bitonic
+//                       network (rank counting for rows > 256 blocks), fp64 sequential prefix sums rounded to
+//                       fp32 (== torch CPU sort(stable)+cumsum, bit-exact), ballot compaction into the
+//                       ascending per-row block-index list.
 //   mask_to_index_kernel   bool mask -> the same index-list format.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -288,15 +290,14 @@ __global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// select: grid ceil(rows/8), 256 threads, one warp per score row.  dynamic smem: 8 * 2 * nk_pad floats.
-// NSLOT = ceil(nk/32) elements per lane, ranks kept in registers (NSLOT == 0: generic two-pass fallback).
+// select, long rows (nk > 256): one warp per score row, O(n^2) rank counting under (value desc, index asc), fp64
+// sequential prefix sums.  dynamic smem: 8 * 2 * nk_pad floats.  Rows of up to 256 blocks take the bitonic kernel.
 // ------------------------------------------------------------------------------------------------
-template <int NSLOT>
-__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int64_t total_rows, int nq, int nk,
-                                                     int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
-                                                     const int32_t* __restrict__ hi_bh, float thr, int force_last,
-                                                     int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
-                                                     uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
+__global__ void __launch_bounds__(256) select_rank_kernel(const float* __restrict__ scores, int64_t total_rows, int nq, int nk,
+                                                          int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
+                                                          const int32_t* __restrict__ hi_bh, float thr, int force_last,
+                                                          int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
+                                                          uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_pad = (nk + 31) & ~31;
@@ -309,11 +310,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   const float* src = scores + row * nk;
   for (int j = lane; j < nk_pad; j += 32) vals[j] = j < nk ? src[j] : -INFINITY;
   __syncwarp();
-
-  // rank of element j under (value desc, index asc): #{i : v_i > v_j or (v_i == v_j and i < j)}.
-  // Padding entries are -inf at indices >= nk, so they never outrank a real element.
-  constexpr int NS = NSLOT > 0 ? NSLOT : 1;
-  int rank[NS];
+  // rank of element j: #{i : v_i > v_j or (v_i == v_j and i < j)}; padding is -inf at indices >= nk
   auto rank_of = [&](int j, float vj) {
     int r = 0;
     for (int i4 = 0; i4 < nk_pad; i4 += 4) {
@@ -325,36 +322,11 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
     }
     return r;
   };
-  if (NSLOT > 0) {
-    float vj[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      vj[s] = vals[s * 32 + lane];
-      rank[s] = 0;
-    }
-    for (int i4 = 0; i4 < nk_pad; i4 += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(vals + i4);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const int j = s * 32 + lane;
-        rank[s] += (v.x > vj[s]) || (v.x == vj[s] && i4 + 0 < j);
-        rank[s] += (v.y > vj[s]) || (v.y == vj[s] && i4 + 1 < j);
-        rank[s] += (v.z > vj[s]) || (v.z == vj[s] && i4 + 2 < j);
-        rank[s] += (v.w > vj[s]) || (v.w == vj[s] && i4 + 3 < j);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (s * 32 + lane < nk) sorted[rank[s]] = vj[s];
-  } else {
-    for (int j = lane; j < nk; j += 32) {
-      const float vj = vals[j];
-      sorted[rank_of(j, vj)] = vj;
-    }
+  for (int j = lane; j < nk; j += 32) {
+    const float vj = vals[j];
+    sorted[rank_of(j, vj)] = vj;
   }
   __syncwarp();
-
-  // fp64 sequential prefix sums, each prefix rounded to fp32 (torch.cumsum on CPU); find the cut.
   const int lo = lo_bh ? lo_bh[bh] : lo_s;
   const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kfirst = nk;
@@ -364,7 +336,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
     const float total = static_cast<float>(acc);
     const float th = __fmul_rn(thr, total);
     acc = 0.0;
-    const int lim = hi < nk ? hi : nk;  // beyond `hi` the clamp decides: no need to look further
+    const int lim = hi < nk ? hi : nk;  // beyond `hi` the clamp decides
     for (int i = 0; i < lim; ++i) {
       acc += static_cast<double>(sorted[i]);
       if (static_cast<float>(acc) >= th) {
@@ -377,22 +349,13 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   int kc = kfirst < lo ? lo : kfirst;
   kc = kc > hi ? hi : kc;
   if (kcut && lane == 0) kcut[row] = kc;
-
   const bool full_row = force_last > 0 && qi >= nq - force_last;
   int32_t* irow = idx + row * nk;
   uint8_t* mrow = mask ? mask + row * nk : nullptr;
   int base = 0;
-  const int nslot = nk_pad / 32;
-  for (int s = 0; s < nslot; ++s) {
+  for (int s = 0; s < nk_pad / 32; ++s) {
     const int j = s * 32 + lane;
-    int rk;
-    if (NSLOT > 0) {
-      rk = 0;
-#pragma unroll
-      for (int u = 0; u < NS; ++u) rk = (u == s) ? rank[u] : rk;
-    } else {
-      rk = rank_of(j, vals[j]);
-    }
+    const int rk = rank_of(j, vals[j]);
     const bool sel = j < nk && (rk < kc || full_row || (force_last > 0 && j >= nk - force_last));
     const unsigned bal = __ballot_sync(0xffffffffu, sel);
     if (sel) irow[base + __popc(bal & ((1u << lane) - 1u))] = j;
@@ -726,8 +689,8 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
   else if (nk <= 256) LAUNCH_BITONIC(8);
   else {  // long rows: O(n^2) rank counting fallback
     if (smem > 48 * 1024)
-      BLADE_CUDA_OK(cudaFuncSetAttribute(select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    select_kernel<0><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
+      BLADE_CUDA_OK(cudaFuncSetAttribute(select_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_rank_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
         scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
         cfg->force_last, idx, cnt, mask_opt, kcut_opt);
   }
