@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--guidance", type=float, default=5.0)
     ap.add_argument("--dense", action="store_true", help="replace ASA by dense SDPA (context number)")
+    ap.add_argument("--model", default="wan", choices=["wan", "cog"], help="wan = config 3, cog = config 5")
+    ap.add_argument("--retain", type=float, default=None, help="cog density sweep: min = max retain ratio")
     a = ap.parse_args()
     import torch.distributed as dist
     from video_blade_b200 import wanx_blocksparseattn as W
@@ -50,21 +52,42 @@ def main():
     branch = 0 if world == 1 else rank // P
 
     torch.manual_seed(0)
-    model = WanLikeDiT(layers=a.layers).to(dev, torch.bfloat16).eval()
-    inner = set_adaptive_block_sparse_attn_wanx(model)
-    inner.print_every = 0
-    model.set_sequence_parallel(group)
-    if a.dense:
-        class Dense(torch.nn.Module):
-            def forward(self, q, k, v):
-                return torch.nn.functional.scaled_dot_product_attention(q, k, v)
-        for blk in model.blocks:
-            blk.attn1.inner_attention = Dense()
 
+    class Dense(torch.nn.Module):
+        def forward(self, q, k, v, **kw):
+            return torch.nn.functional.scaled_dot_product_attention(q, k, v)
     g = torch.Generator(device="cpu").manual_seed(1)
-    noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
-    prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
-    negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+    if a.model == "cog":
+        assert world == 1, "the CogVideoX scaffold is single-GPU (its Ulysses processor is not written)"
+        from video_blade_b200 import cogvideo_blocksparseattn as Cg
+        from video_blade_b200.dit import CogLikeDiT
+        from video_blade_b200.modify_cogvideo import set_block_sparse_attn_cogvideox
+        if a.retain is not None:
+            Cg.max_retain_ratio = Cg.min_retain_ratio = a.retain
+        layers = 42 if a.layers == 30 else a.layers
+        with torch.device(dev):
+            model = CogLikeDiT(layers=layers).to(torch.bfloat16).eval()
+        blocks = model.transformer_blocks
+        inner = set_block_sparse_attn_cogvideox(model)
+        noise = torch.randn(1, 13, 16, 60, 90, generator=g).to(dev, torch.bfloat16)
+        prompt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
+        negative = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
+        wname = f"CogVideoX-5B 49x480x720, {layers} DiT blocks, 8 steps, CFG batch 2" + \
+                (f", min=max retain {a.retain}" if a.retain is not None else "")
+    else:
+        layers = a.layers
+        model = WanLikeDiT(layers=a.layers).to(dev, torch.bfloat16).eval()
+        blocks = model.blocks
+        inner = set_adaptive_block_sparse_attn_wanx(model)
+        model.set_sequence_parallel(group)
+        noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
+        prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+        negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+        wname = f"Wan2.1-T2V-1.3B 81x480x832, {layers} DiT blocks, 8 steps, CFG batch 2"
+    inner.print_every = 0
+    if a.dense:
+        for blk in blocks:
+            blk.attn1.inner_attention = Dense()
     cfg_ranks = None if world == 1 else (branch, 0, P)
     vel = make_velocity_fn(model, prompt, negative, a.guidance, cfg_ranks)
 
@@ -88,10 +111,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        line = {"metric": "8-step clip seconds (Wan2.1-T2V-1.3B shape, random init, CFG, synthetic inputs)",
+        line = {"metric": f"8-step clip seconds ({'CogVideoX-5B' if a.model == 'cog' else 'Wan2.1-T2V-1.3B'} shape, random init, CFG, synthetic inputs)",
                 "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
-                "config": {"workload": "Wan2.1-T2V-1.3B 81x480x832, 30 DiT blocks, 8 steps, CFG batch 2",
-                           "layers": a.layers, "steps": a.steps, "attention": "dense SDPA" if a.dense else "ASA",
+                "config": {"workload": wname,
+                           "layers": layers, "steps": a.steps, "attention": "dense SDPA" if a.dense else "ASA",
                            "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}"},
                 "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
                 "avg_sparsity": None if a.dense else inner.average_sparsity()}

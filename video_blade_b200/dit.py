@@ -225,3 +225,85 @@ def generate_new(velocity_fn, noise, steps=8, eta=1.0, flow_shift=3.0, total_ste
         s2 = flow_sigma(T.clamp(min=0), flow_shift, total_steps).view(B, 1, 1, 1, 1).to(x_t.dtype)
         x_t = (1 - s2) * latent + s2 * add_eps                    # add_noise(latent, add_eps, T)  (TW:1437)
     return latent
+
+
+# ================================================================================================
+# CogVideoX-5B-shaped scaffold (BASELINE config 5): 42 blocks, dim 3072, 48 heads x 64, joint text+video
+# self-attention (226 text tokens in front, MC:35), adaLN-zero modulation of both streams, 3-axis RoPE on the video
+# tokens only.  Same caveats as WanLikeDiT: random init, stock torch ops everywhere except `inner_attention`.
+# ================================================================================================
+class _LayerNormZero(nn.Module):
+    """CogVideoXLayerNormZero: one linear on the time embedding -> shift/scale/gate for video and text."""
+
+    def __init__(self, dim, temb_dim):
+        super().__init__()
+        self.linear = nn.Linear(temb_dim, 6 * dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-5, elementwise_affine=True)
+
+    def forward(self, x, txt, temb):
+        sh, sc, g, tsh, tsc, tg = self.linear(F.silu(temb)).chunk(6, dim=1)
+        x = self.norm(x) * (1 + sc[:, None]) + sh[:, None]
+        txt = self.norm(txt) * (1 + tsc[:, None]) + tsh[:, None]
+        return x, txt, g[:, None], tg[:, None]
+
+
+class CogBlock(nn.Module):
+    def __init__(self, dim, heads, temb_dim):
+        super().__init__()
+        self.norm1 = _LayerNormZero(dim, temb_dim)
+        self.attn1 = Attention(dim, heads, qk_norm="layer_norm")
+        self.norm2 = _LayerNormZero(dim, temb_dim)
+        self.ff = nn.Sequential(nn.Linear(dim, 4 * dim), nn.GELU(approximate="tanh"), nn.Linear(4 * dim, dim))
+
+    def forward(self, x, txt, temb, rope):
+        T = txt.shape[1]
+        nx, nt, g, tg = self.norm1(x, txt, temb)
+        ax, at = self.attn1(nx, encoder_hidden_states=nt, image_rotary_emb=rope)
+        x, txt = x + g * ax, txt + tg * at
+        nx, nt, g, tg = self.norm2(x, txt, temb)
+        ff = self.ff(torch.cat([nt, nx], dim=1))
+        return x + g * ff[:, T:], txt + tg * ff[:, :T]
+
+
+def rope_cos_sin(frames, height, width, head_dim, theta=10000.0, device="cpu"):
+    """(cos, sin) [S, head_dim] with repeat-interleaved pairs, the layout diffusers hands the CogVideoX processor."""
+    f = rope_freqs(frames, height, width, head_dim, theta, device)[0, 0]          # complex [S, D/2]
+    return f.real.float().repeat_interleave(2, -1).contiguous(), f.imag.float().repeat_interleave(2, -1).contiguous()
+
+
+class CogLikeDiT(nn.Module):
+    def __init__(self, dim=3072, heads=48, layers=42, text_dim=4096, in_ch=16, patch=2, temb_dim=512):
+        super().__init__()
+        self.dim, self.heads, self.in_ch, self.patch = dim, heads, in_ch, patch
+        self.patch_embedding = nn.Linear(in_ch * patch * patch, dim)
+        self.text_proj = nn.Linear(text_dim, dim)
+        self.time_embedding = nn.Sequential(nn.Linear(dim, temb_dim), nn.SiLU(), nn.Linear(temb_dim, temb_dim))
+        self.transformer_blocks = nn.ModuleList([CogBlock(dim, heads, temb_dim) for _ in range(layers)])
+        self.norm_final = nn.LayerNorm(dim, eps=1e-5)
+        self.norm_out_linear = nn.Linear(temb_dim, 2 * dim)
+        self.norm_out = nn.LayerNorm(dim, eps=1e-5, elementwise_affine=False)
+        self.proj_out = nn.Linear(dim, in_ch * patch * patch)
+        self._rope = {}
+
+    def forward(self, hidden_states, timestep, encoder_hidden_states):
+        """hidden_states [B,F,C,H,W] latents (CogVideoX layout); encoder_hidden_states [B,226,4096]."""
+        B, Fr, C, H, W = hidden_states.shape
+        p = self.patch
+        x = hidden_states.view(B, Fr, C, H // p, p, W // p, p).permute(0, 1, 3, 5, 2, 4, 6)
+        x = self.patch_embedding(x.reshape(B, Fr * (H // p) * (W // p), C * p * p))
+        txt = self.text_proj(encoder_hidden_states)
+        half = self.dim // 2
+        fr = torch.exp(-math.log(10000.0) * torch.arange(half, device=x.device, dtype=torch.float32) / half)
+        args = timestep.float()[:, None] * fr[None]
+        temb = self.time_embedding(torch.cat([torch.cos(args), torch.sin(args)], -1).type_as(x))
+        key = (Fr, H // p, W // p, str(x.device))
+        if key not in self._rope:
+            self._rope[key] = rope_cos_sin(Fr, H // p, W // p, self.dim // self.heads, device=x.device)
+        rope = self._rope[key]
+        for blk in self.transformer_blocks:
+            x, txt = blk(x, txt, temb, rope)
+        x = self.norm_final(x)
+        sh, sc = self.norm_out_linear(F.silu(temb)).chunk(2, dim=1)
+        x = self.proj_out(self.norm_out(x) * (1 + sc[:, None]) + sh[:, None])
+        x = x.view(B, Fr, H // p, W // p, C, p, p).permute(0, 1, 4, 2, 5, 3, 6)
+        return x.reshape(B, Fr, C, H, W)
