@@ -427,19 +427,18 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           if (wq == 0) TRACE(t, 2, g);
           const float neg_m = (m == -INFINITY) ? 0.f : -m;  // all-masked so far: exp2(-inf - 0) = 0, never NaN
-          float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent sum chains
+          // packed fp32x2 math: x = s * scale - m and the row-sum accumulation take one issue slot per PAIR
+          const uint64_t sl2_2 = pack_f32x2(sl2, sl2), negm_2 = pack_f32x2(neg_m, neg_m);
+          uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};  // four independent packed sum chains
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              // exp2 is split between the MUFU pipe and a polynomial on the FMA pipe (kPolyMask picks which
-              // of every 8 elements take the polynomial): MUFU alone (16/clk/SM) costs as much as the MMAs.
-              const float x0 = fmaf(__uint_as_float(s[c][2 * i]), sl2, neg_m);
-              const float x1 = fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, neg_m);
-              const float p0 = ((kPolyMask >> ((2 * i) & 7)) & 1) ? ex2_poly(x0) : ex2_approx(x0);
-              const float p1 = ((kPolyMask >> ((2 * i + 1) & 7)) & 1) ? ex2_poly(x1) : ex2_approx(x1);
-              ls[i & 3] += p0 + p1;
+              const uint64_t x = fma_f32x2(pack_u32x2(s[c][2 * i], s[c][2 * i + 1]), sl2_2, negm_2);
+              const float p0 = ex2_approx(lo_f32(x));
+              const float p1 = ex2_approx(hi_f32(x));
+              ls2[i & 3] = add_f32x2(ls2[i & 3], pack_f32x2(p0, p1));
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }
             if (c == 2) {
@@ -452,6 +451,8 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             tmem_st16(tS + c * 16, pk);
           }
+          const uint64_t lsa = add_f32x2(add_f32x2(ls2[0], ls2[1]), add_f32x2(ls2[2], ls2[3]));
+          float ls[4] = {lo_f32(lsa), hi_f32(lsa), 0.f, 0.f};
           l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
           if (wq == 0) TRACE(t, 3, g);
           tmem_wait_st();

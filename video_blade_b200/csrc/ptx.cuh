@@ -234,6 +234,26 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.9999289512634277f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
+// packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of work; operands are 64-bit register pairs
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  return static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float lo_f32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi_f32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+
 // pack two fp32 into bf16x2: lo -> bits [0,16), hi -> bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
