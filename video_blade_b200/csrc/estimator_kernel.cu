@@ -195,29 +195,34 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (j < 256) myR[j] = IS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(bm)) : __half_as_ushort(__float2half_rn(bm));
       }
     }
-    // Po[i, j] = max over the 32 rows of q-block i (= this warp) of exp2(R[r,j] - m[r]); lane j%32 keeps column j
+    // Po[i, j] = max over the 32 rows of q-block i (= this warp) of exp2(R[r,j] - m[r]), stored in q.dtype (P:72-82).
+    // Rounding is monotonic, so each thread first overwrites its own R row in place with the ROUNDED exponentials
+    // (one MUFU per entry, no cross-lane traffic); then lane L takes the column maxima of columns j = 32*jj + L over
+    // the 32 rows of its warp's block straight from shared memory (conflict-free: consecutive lanes read
+    // consecutive 16-bit words of one padded row).
     const int qblk = qt * 4 + warp;
+    for (int j = 0; j < nb; ++j) {
+      const float r = IS_BF16 ? __bfloat162float(__ushort_as_bfloat16(myR[j])) : __half2float(__ushort_as_half(myR[j]));
+      const float e = ex2_approx(r - m);
+      myR[j] = IS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(e)) : __half_as_ushort(__float2half_rn(e));
+    }
+    __syncwarp();
     float po[8];
     float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) po[jj] = 0.f;
+    const uint16_t* blkR = sR + (warp * 32) * L::kRStride;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const int j0 = jj * 32;
-      if (j0 >= nb) break;
-      float keep = 0.f;
-      for (int jl = 0; jl < 32; ++jl) {
-        const int j = j0 + jl;
-        if (j >= nb) break;
-        const float r = IS_BF16 ? __bfloat162float(__ushort_as_bfloat16(myR[j])) : __half2float(__ushort_as_half(myR[j]));
-        float e = ex2_approx(r - m);
-#pragma unroll
-        for (int off = 16; off; off >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, off));
-        if (jl == lane) keep = e;
+      const int j = jj * 32 + lane;
+      float mxv = 0.f;  // exponentials are >= 0
+      if (j < nb) {
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const uint16_t u = blkR[rr * L::kRStride + j];
+          mxv = fmaxf(mxv, IS_BF16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u)));
+        }
+        sum += mxv;
       }
-      keep = IS_BF16 ? bf16_round(keep) : __half2float(__float2half_rn(keep));  // Po is stored in q.dtype (P:80)
-      po[jj] = keep;
-      if (j0 + lane < nb) sum += keep;
+      po[jj] = mxv;
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
