@@ -128,7 +128,7 @@ def traffic_bytes():
 
 
 def make_inputs(B, H, S, D, kind, seed, grid, text_length=0):
-    from oracle.asa_oracle import synth_qkv     # synthetic-input recipe shared with the tests (not timed)
+    from video_blade_b200.synth import synth_qkv     # synthetic-input recipe shared with the tests (not timed)
     q, k, v = synth_qkv(B, H, S, D, seed=seed, structured=2.0 if kind == "structured" else 0.0, grid=grid,
                         text_length=text_length)
     # the reference hands the module transposed views of [B,S,H,D] memory (modify_wan.py:104-106)
@@ -137,7 +137,7 @@ def make_inputs(B, H, S, D, kind, seed, grid, text_length=0):
 
 def algorithmic_flops(cnt, mask_last_col, S, D, n_pool, block=128):
     """4*D*sum rows_i*(sum selected cols_j + n_pool), ragged tails at true size."""
-    from oracle.asa_oracle import attention_flops
+    from video_blade_b200.synth import attention_flops
     nb = cnt.shape[-1]
     cols = cnt.float() * block
     tail = S - (nb - 1) * block
