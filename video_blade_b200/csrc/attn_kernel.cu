@@ -17,12 +17,18 @@
 //                    128-column S row, online softmax in registers with lazy O rescale (threshold 2^8),
 //                    tcgen05.st of P, final normalise + merge + (inverse-Gilbert) row store;
 //   * TMEM map (512 columns): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [256+D,256+2D).
+//   * tail round: when the last round of pair items would occupy at most half of the CTAs, those pairs are
+//     issued as "solo" items instead -- ONE query tile per CTA whose KV sequence is split between the two
+//     streams (stream 0: pooled tiles + first part of the list, stream 1: the rest); warpgroup 0 reads both
+//     accumulators straight from TMEM (same lanes) and folds them with the usual (m, l) rescale.  Each stream
+//     is bound by its own softmax -> MMA latency chain, so halving the chain halves the tail round.
 //
 // All synchronisation is mbarrier based (TMA complete_tx, tcgen05.commit, thread arrivals).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -55,7 +61,7 @@ constexpr int kRegsOther = 56;
 #define BLADE_POLY_MASK 0x00  // bit i set: element i of every 8 uses ex2_poly.  Measured on B200 (profiles/README.md): 0x00 1.22 ms, 0x22 1.25, 0x2A 1.32, 0xAA 1.37 -> off
 #endif
 constexpr unsigned kPolyMask = BLADE_POLY_MASK;
-constexpr int kMaxListSmem = 256;       // per-stream block ids cached in smem by the producer
+constexpr int kMaxListSmem = 128;       // per-stream block ids cached in smem by the producer (longer lists: __ldg)
 constexpr float kLn2 = 0.69314718055994530942f;
 
 template <int D>
@@ -76,6 +82,7 @@ struct Misc {
   uint32_t tmem_base;
   uint32_t pad;
   uint16_t list[2][kMaxListSmem];
+  float2 ml[kBlockM];  // solo items: stream 1's (m, l) per query row, handed to warpgroup 0
 };
 static_assert(sizeof(Misc) <= 2048, "misc smem region overflow");
 
@@ -91,6 +98,7 @@ struct AttnParams {
   int B, H, S, nq, nk;
   int n_pool, n_pool_tiles;
   int num_items, pairs_per_head;
+  int num_pair_items;      // items [0, num_pair_items) are tile pairs, the rest are solo tiles (two per pair id)
   float scale_log2;        // softmax_scale * log2(e)
   float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
   float gap;               // float(sample_gap) for the non-emulated merge
@@ -118,6 +126,54 @@ __device__ __forceinline__ float2 unpack_t(uint32_t w) {
 template <int D>
 __device__ __forceinline__ uint32_t kmajor_koff(int k) {
   return static_cast<uint32_t>((k >> 2) * (kBlockN * 128 / 16) + (k & 3) * 2);
+}
+
+// One work item as the three roles see it: per stream t its query tile, how many pooled tiles it runs first,
+// and which slice [off, off + ns) of the row's block list it owns.
+struct Item {
+  int bh;
+  int qb[2], pt[2], off[2], ns[2];
+  bool merge;  // solo item with work on both streams: warpgroup 0 folds stream 1's accumulator into its own
+};
+__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+  Item it;
+  const int npt = p.n_pool_tiles;
+  if (item < p.num_pair_items) {
+    it.bh = item / p.pairs_per_head;
+    const int pair = item % p.pairs_per_head;
+    it.merge = false;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int qb = 2 * pair + t;
+      const bool valid = qb < p.nq;
+      it.qb[t] = qb;
+      it.pt[t] = valid ? npt : 0;
+      it.off[t] = 0;
+      it.ns[t] = valid ? __ldg(p.cnt + static_cast<int64_t>(it.bh) * p.nq + qb) : 0;
+    }
+  } else {
+    const int s = item - p.num_pair_items;
+    const int pid = p.num_pair_items + (s >> 1);
+    it.bh = pid / p.pairs_per_head;
+    const int qb = 2 * (pid % p.pairs_per_head) + (s & 1);
+    const bool valid = qb < p.nq;
+    const int c = valid ? __ldg(p.cnt + static_cast<int64_t>(it.bh) * p.nq + qb) : 0;
+    // balance pooled + a  against  c - a tiles
+    int a = c;
+    if (c >= 2) {
+      a = (c - npt) / 2;
+      a = a < 1 ? 1 : (a > c - 1 ? c - 1 : a);
+    }
+    it.qb[0] = it.qb[1] = qb;
+    it.pt[0] = valid ? npt : 0;
+    it.pt[1] = 0;
+    it.off[0] = 0;
+    it.ns[0] = a;
+    it.off[1] = a;
+    it.ns[1] = c - a;
+    it.merge = c - a > 0;
+  }
+  return it;
 }
 
 // ================================================================================================
@@ -180,18 +236,17 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t slot = 0, ph = 0;  // ring position / phase of the NEXT load
     uint32_t q_it[2] = {0, 0};
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+      const Item it = decode_item(p, item);
+      const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
       int ns[2], nt[2];
       const int32_t* lists[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int qb = 2 * pair + t;
-        const bool valid = qb < p.nq;
-        const int64_t row = static_cast<int64_t>(bh) * p.nq + qb;
-        ns[t] = valid ? __ldg(p.cnt + row) : 0;
-        nt[t] = valid ? npt + ns[t] : 0;
-        lists[t] = p.idx + row * p.idx_stride;
+        const int64_t row = static_cast<int64_t>(bh) * p.nq + it.qb[t];
+        ns[t] = it.ns[t];
+        nt[t] = it.pt[t] + it.ns[t];
+        lists[t] = p.idx + row * p.idx_stride + it.off[t];
         // cooperative, coalesced fetch of the block-id list into smem (private to this warp)
         for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32)
           mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j) & 0x0FFFFFFF);
@@ -206,7 +261,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int dh = 0; dh < kSub; ++dh)
             tma_load_4d(sQ + t * kTileBytes + dh * (kBlockM * 128), &tmQ, &mz->q_full[t], dh * 64,
-                        (2 * pair + t) * kBlockM, h, b, kEvictFirst);
+                        it.qb[t] * kBlockM, h, b, kEvictFirst);
         }
         __syncwarp();
         ++q_it[t];
@@ -215,11 +270,11 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&mz->kv_empty[slot], ph ^ 1);
         const CUtensorMap* map;
         int row;
-        if (j < npt) {
+        if (j < it.pt[t]) {
           map = is_v ? &tmVp : &tmKp;
           row = j * kBlockN;
         } else {
-          const int jj = j - npt;
+          const int jj = j - it.pt[t];
           const int kb = jj < kMaxListSmem ? static_cast<int>(mz->list[t][jj]) : (__ldg(lists[t] + jj) & 0x0FFFFFFF);
           map = is_v ? &tmV : &tmK;
           row = kb * kBlockN;
@@ -260,13 +315,8 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t q_it[2] = {0, 0};
     const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
-      int nt[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int qb = 2 * pair + t;
-        nt[t] = qb < p.nq ? npt + __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb) : 0;
-      }
+      const Item it = decode_item(p, item);
+      const int nt[2] = {it.pt[0] + it.ns[0], it.pt[1] + it.ns[1]};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (nt[t] == 0) continue;
@@ -335,7 +385,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j < nt[t]) {
-            issue_pv(t, j == 0 || j == npt);
+            issue_pv(t, j == 0 || j == it.pt[t]);
             if (j + 1 < nt[t]) issue_qk(t, j + 2 == nt[t]);
           }
         }
@@ -357,18 +407,23 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int seq_tail = p.S - (p.nk - 1) * kBlockN;  // valid keys in the last key block
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+      const Item it = decode_item(p, item);
+      const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
-      const int qb = 2 * pair + t;
+      const int qb = t ? it.qb[1] : it.qb[0];  // selects, not indexing: keeps Item in registers
       if (qb >= p.nq) continue;
-      const int64_t lrow = static_cast<int64_t>(bh) * p.nq + qb;
-      const int ns = __ldg(p.cnt + lrow);
-      const int last_kb = ns > 0 ? (__ldg(p.idx + lrow * p.idx_stride + ns - 1) & 0x0FFFFFFF) : -1;
+      const bool solo = item >= p.num_pair_items;
+      if (solo && t == 1 && !it.merge) continue;  // nothing to split: stream 0 runs the whole tile alone
+      const int my_pt = t ? it.pt[1] : it.pt[0];
+      const int ns = t ? it.ns[1] : it.ns[0];
+      const int32_t* my_list =
+          p.idx + (static_cast<int64_t>(bh) * p.nq + qb) * p.idx_stride + (t ? it.off[1] : it.off[0]);
+      const int last_kb = ns > 0 ? (__ldg(my_list + ns - 1) & 0x0FFFFFFF) : -1;
       const int sparse_tail = (last_kb == p.nk - 1) ? seq_tail : kBlockN;
       float lse2 = 0.f;
 
-      for (int phase = (npt ? 0 : 1); phase < 2; ++phase) {
-        const int ntile = phase == 0 ? npt : ns;
+      for (int phase = (my_pt ? 0 : 1); phase < 2; ++phase) {
+        const int ntile = phase == 0 ? my_pt : ns;
         const int tail_valid = phase == 0 ? pool_tail : sparse_tail;
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < ntile; ++j, ++g) {
@@ -385,7 +440,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // 64x64 mask granularity (block_size 64): bits (2*rowhalf + colhalf) of the entry's quadrant mask
           unsigned cmask = 3u;
           if (p.sub64 && phase == 1)
-            cmask = (static_cast<unsigned>(__ldg(p.idx + lrow * p.idx_stride + j)) >> (28 + 2 * (wq >> 1))) & 3u;
+            cmask = (static_cast<unsigned>(__ldg(my_list + j)) >> (28 + 2 * (wq >> 1))) & 3u;
           if (valid < kBlockN || cmask != 3u) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -464,8 +519,30 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---- phase finalisation: the last PV of this phase has to retire first
         mbar_wait(&mz->o_full[t], (g - 1) & 1);
         tc_fence_after();
+        if (it.merge && t == 1) {
+          // solo item, second half of the list: hand (m, l) to warpgroup 0, which reads O1 from TMEM itself
+          mz->ml[row_in_tile] = make_float2(m, l);
+          tc_fence_before();
+          named_bar_arrive<1, 2 * kSoftmaxThreads>();
+          named_bar_sync<2, 2 * kSoftmaxThreads>();  // O1 has been read: the next item may overwrite it
+          continue;
+        }
+        float w1 = 0.f;  // weight of stream 1's accumulator (solo items)
+        float a0 = 1.f;
+        if (it.merge && phase == 1) {
+          named_bar_sync<1, 2 * kSoftmaxThreads>();
+          tc_fence_after();
+          const float2 ml1 = mz->ml[row_in_tile];
+          const float mm = fmaxf(m, ml1.x);
+          a0 = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
+          w1 = (ml1.x == -INFINITY) ? 0.f : ex2_approx(ml1.x - mm);
+          l = a0 * l + w1 * ml1.y;
+          m = mm;
+        }
         const float inv_l = 1.0f / l;
         const float lse = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
+        const float w0 = a0 * inv_l;
+        w1 *= inv_l;
         if (phase == 0) {
           lse2 = lse;
 #pragma unroll
@@ -510,12 +587,23 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < D / 32; ++c) {
             uint32_t o[32];
             tmem_ld32(tO + c * 32, o);
-            tmem_wait_ld();
+            if (it.merge) {
+              uint32_t o1[32];
+              tmem_ld32(tO + D + c * 32, o1);  // stream 1's accumulator: same lanes, next D columns
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                o[i] = __float_as_uint(__uint_as_float(o[i]) * w0 + __uint_as_float(o1[i]) * w1);
+            } else {
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * w0);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * u + i]) * inv_l;
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * u + i]);
               if (npt) {
                 const uint4 w2 = park[(c * 4 + u) * kBlockM + row_in_tile];
                 const uint32_t ww[4] = {w2.x, w2.y, w2.z, w2.w};
@@ -542,6 +630,10 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               w.w = pack_t<IS_BF16>(f[6], f[7]);
               if (store) reinterpret_cast<uint4*>(orow)[c * 4 + u] = w;
             }
+          }
+          if (it.merge) {
+            tc_fence_before();
+            named_bar_arrive<2, 2 * kSoftmaxThreads>();
           }
         }
         // O_t / S_t are handed back implicitly: the next PV of this stream waits for our next p_full.
@@ -726,7 +818,16 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.n_pool = n_pool;
   p.n_pool_tiles = pooled ? (int)ceil_div(n_pool, kBlockN) : 0;
   p.pairs_per_head = (nq + 1) / 2;
-  p.num_items = (int)(B * H) * p.pairs_per_head;
+  {
+    // tail round: if the leftover pairs would fill at most half of the CTAs, run them as solo tiles with the KV
+    // list split across the two streams (BLADE_NO_SPLIT=1 disables, for A/B timing)
+    static const bool no_split = getenv("BLADE_NO_SPLIT") && atoi(getenv("BLADE_NO_SPLIT")) != 0;
+    const int np = (int)(B * H) * p.pairs_per_head, G = device_sm_count();
+    const int r = np % G;
+    const int split = (!no_split && r > 0 && 2 * r <= G) ? r : 0;
+    p.num_pair_items = np - split;
+    p.num_items = p.num_pair_items + 2 * split;
+  }
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.gap = (float)sample_gap;
   p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;

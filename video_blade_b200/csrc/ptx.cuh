@@ -267,6 +267,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// named CTA barriers (id 1..15; id 0 is __syncthreads): kThreads = arriving + waiting threads
+template <int kId, int kThreads>
+__device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kThreads) : "memory");
+}
+template <int kId, int kThreads>
+__device__ __forceinline__ void named_bar_arrive() {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"n"(kId), "n"(kThreads) : "memory");
+}
+
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
