@@ -448,3 +448,73 @@ def test_select_long_rows_fallback():
     assert torch.equal(mask.cpu(), want)
     widx, wcnt = O.mask_to_index_list(want)
     assert torch.equal(idx.cpu(), widx) and torch.equal(cnt.cpu(), wcnt)
+
+
+# ------------------------------------------------------------------ work-item scheduling modes of the attention kernel
+def test_solo_items_with_tiny_lists():
+    """Few tiles -> every item is a 'solo' tile whose list is split across the two streams: rows with 1 entry
+    (no split possible), 2, 3 ... entries, with and without the pooled branch."""
+    eng = _engine(use_rearrange=False, sample_gap=30)
+    S, H, D = 1024, 2, 128
+    q, k, v = O.synth_qkv(1, H, S, D, seed=5)
+    nb = S // 128
+    mask = torch.zeros(1, H, nb, nb, dtype=torch.bool)
+    for r in range(nb):
+        mask[0, 0, r, : r + 1] = True            # 1, 2, 3 ... 8 entries
+        mask[0, 1, r, r] = True                  # always 1 entry
+    mask[0, 1, 3, :] = True
+    idx, cnt = O.mask_to_index_list(mask)
+    out, lse = eng.block_sparse_attn(q.cuda(), k.cuda(), v.cuda(), idx.cuda(), cnt.cuda())
+    wout, wlse = O.dense_masked_attention(q, k, v, mask)
+    _close(out, wout)
+    _close(lse, wlse, 1e-5, 1e-4)
+    kp, vp = O.simple_pooling(k, 30), O.simple_pooling(v, 30)
+    out2 = eng.asa_attn(q.cuda(), k.cuda(), v.cuda(), idx.cuda(), cnt.cuda(), kp.cuda(), vp.cuda())
+    o2, l2 = O.standard_attn(q, kp, vp)
+    want = O.merge_lse(wout, wlse.unsqueeze(-1).to(q.dtype), o2, l2.unsqueeze(-1).to(q.dtype), 30)
+    _close(out2, want)
+
+
+@pytest.mark.parametrize("H,Sq", [(1, 1024), (10, 2048)])
+def test_long_lists_beyond_smem_cache(H, Sq):
+    """Key lists longer than the producer's 128-entry smem cache (the __ldg path), ragged last key block, Sq != Sk;
+    H=1 runs as solo items (lists split 150/150), H=10 as tile pairs (80 pairs on 148 CTAs).  All-ones mask ==
+    plain attention (W:21-24), checked against fp32 SDPA."""
+    eng = _engine(use_rearrange=False)
+    Sk, D = 300 * 128 - 37, 128
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(1, H, Sq, D, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(1, H, Sk, D, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(1, H, Sk, D, generator=g).to(torch.bfloat16).cuda()
+    nq, nk = Sq // 128, 300
+    mask = torch.ones(1, H, nq, nk, dtype=torch.bool, device="cuda")
+    idx, cnt = eng.mask_to_index(mask)
+    assert int(cnt.min()) == 300
+    out, lse = eng.block_sparse_attn(q, k, v, idx, cnt)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    _close(out, ref.to(q.dtype))
+    s = (q[:, :, :4].float() @ k.float().transpose(-1, -2)) / D ** 0.5
+    _close(lse[:, :, :4], torch.logsumexp(s, -1), 1e-5, 1e-4)
+
+
+def test_split_tail_matches_unsplit_schedule():
+    """The tail round split (solo items) is a scheduling choice: with BLADE_NO_SPLIT=1 read by a fresh library
+    instance the same inputs must give the same output within fp32 re-association of the two partial softmaxes."""
+    import os, subprocess, sys
+    code = (
+        "import torch, sys; sys.path.insert(0, '.');"
+        "from video_blade_b200.asa import AsaEngine, AsaKnobs;"
+        "from video_blade_b200.synth import synth_qkv;"
+        "eng = AsaEngine(AsaKnobs.wan(width=26, height=15, depth=8, max_retain_ratio=0.4));"
+        "q, k, v = synth_qkv(1, 2, 26*15*8, 128, seed=9);"
+        "out, cnt = eng.forward(q.cuda(), k.cuda(), v.cuda());"
+        "torch.save(out.float().cpu(), sys.argv[1])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        path = os.path.join(root, "tests", f"_split_{flag}.pt")
+        env = dict(os.environ, BLADE_NO_SPLIT=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=env, timeout=300)
+        outs.append(torch.load(path))
+        os.remove(path)
+    _close(outs[0], outs[1], 4e-3, 1.6e-2)

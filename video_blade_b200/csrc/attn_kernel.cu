@@ -95,7 +95,7 @@ struct AttnParams {
   float* lse;              // optional fp32 [B,H,S] (sparse-branch lse), may be null
   const int32_t* dst_row;  // optional
   uint4* park;             // [grid][2][D/8][128] 16-byte chunks (pooled-branch output)
-  int B, H, S, nq, nk;
+  int B, H, S, Sk, nq, nk;
   int n_pool, n_pool_tiles;
   int num_items, pairs_per_head;
   int num_pair_items;      // items [0, num_pair_items) are tile pairs, the rest are solo tiles (two per pair id)
@@ -404,7 +404,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t g = 0;
     const float sl2 = p.scale_log2;
     const int pool_tail = p.n_pool - (npt - 1) * kBlockN;
-    const int seq_tail = p.S - (p.nk - 1) * kBlockN;  // valid keys in the last key block
+    const int seq_tail = p.Sk - (p.nk - 1) * kBlockN;  // valid keys in the last key block
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item(p, item);
@@ -813,6 +813,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.B = (int)B;
   p.H = (int)H;
   p.S = (int)S;
+  p.Sk = (int)Sk;
   p.nq = nq;
   p.nk = nk;
   p.n_pool = n_pool;
