@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace blade {
@@ -95,7 +97,9 @@ static void gilbert_fill(int W, int H, int D, int64_t* curve2raster) {
   }
 }
 
-// side stream + events for the fork/join inside blade_asa_forward (created once per process and device)
+// side stream + events for the fork/join inside blade_asa_forward (created once per process and device).  The side
+// stream has the HIGHEST priority: it carries the short latency-bound score and selection kernels, whose CTAs the
+// block scheduler then places ahead of the pending CTAs of the grid-filling, DRAM-bound pooling kernel.
 struct ForkState {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -106,7 +110,9 @@ static ForkState* fork_state() {
   cudaGetDevice(&dev);
   ForkState* f = &st[dev & 15];
   if (!f->side) {
-    cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking);
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, greatest);
     cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming);
   }
@@ -221,28 +227,38 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
                         stream))
     return e;
-  // ... then the bandwidth-bound gap pooling forks onto a side stream and overlaps the latency-bound score and
-  // selection kernels; it is joined again right before the attention launch (events only, no host sync).
-  ForkState* fk = np ? fork_state() : nullptr;
-  if (np) {
+  // ... then the bandwidth-bound gap pooling and the latency-bound score + selection kernels run concurrently on
+  // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):
+  // 0 = pooling on the side stream, 1 = score/selection on the (high-priority) side stream, 2 = no fork.
+  static const int fork_mode = getenv("BLADE_FORK_MODE") ? atoi(getenv("BLADE_FORK_MODE")) : 0;
+  ForkState* fk = (np && fork_mode != 2) ? fork_state() : nullptr;
+  cudaStream_t mstream = stream, pstream = stream;  // streams of the mask kernels / the pooling kernel
+  if (fk) {
+    if (fork_mode == 1) mstream = fk->side; else pstream = fk->side;
     BLADE_CUDA_OK(cudaEventRecord(fk->fork, stream));
     BLADE_CUDA_OK(cudaStreamWaitEvent(fk->side, fk->fork, 0));
-    if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
-                          rearr ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool,
-                          cfg->block_size, cfg->sample_gap, nullptr, 0, 2, fk->side))
-      return e;
-    BLADE_CUDA_OK(cudaEventRecord(fk->join, fk->side));
   }
+  auto run_pool = [&]() -> int {
+    return prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
+                     rearr ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool, cfg->block_size,
+                     cfg->sample_gap, nullptr, 0, 2, pstream);
+  };
+  if (np && fork_mode != 1)
+    if (int e = run_pool()) return e;
   const float* sc = scores_in;
   if (!sc) {
-    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, stream)) return e;
+    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, mstream)) return e;
     sc = scores;
   } else if (scores_out) {
-    BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, stream));
+    BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, mstream));
   }
-  if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, stream)) return e;
-
-  if (np) BLADE_CUDA_OK(cudaStreamWaitEvent(stream, fk->join, 0));
+  if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, mstream)) return e;
+  if (np && fork_mode == 1)
+    if (int e = run_pool()) return e;
+  if (fk) {
+    BLADE_CUDA_OK(cudaEventRecord(fk->join, fk->side));
+    BLADE_CUDA_OK(cudaStreamWaitEvent(stream, fk->join, 0));
+  }
   BladeTensor qr = *q, kr = *k, vr = *v;
   if (rearr) {
     const int64_t cs[4] = {H * S * D, S * D, D, 1};

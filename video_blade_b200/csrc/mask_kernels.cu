@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
   constexpr int LPR = D / 8;
   constexpr int RPW = 32 / LPR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 8 + warp;
+  // reverse traversal: the pooling runs right after the gather kernel, whose LAST writes (high b, h, rows) are the
+  // ones still resident in L2
+  const int g = (gridDim.x - 1 - blockIdx.x) * 8 + warp;
   if (g >= np) return;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = gridDim.y - 1 - blockIdx.y, b = gridDim.z - 1 - blockIdx.z;
   const int sub = lane / LPR, chunk = lane % LPR;
   const float inv = 1.0f / static_cast<float>(gap);
 #pragma unroll
@@ -223,70 +225,106 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// scores: grid (ceil(nb/8), B*H), 256 threads, one warp per score row; the head's K means stream through
-// shared memory in chunks of 32 key blocks (coalesced float4 loads, rows padded to D+4 floats so that the
-// per-lane float4 reads are bank-conflict free).  dynamic smem: (8*(D+nb) + 32*(D+4)) floats
+// scores: grid (ceil(nb/16), B*H), 256 threads.  A CTA owns 16 score rows of one head; the head's K means stream
+// through shared memory in chunks of 64 key blocks (prefetched global -> registers while the previous chunk is
+// multiplied; rows padded to D+4 floats so that the per-lane float4 reads are bank-conflict free).  Thread
+// (qg, kk) = (tid / 64, tid % 64) computes the 4 dot products of query rows 4qg..4qg+3 with key row kk of the
+// chunk: one conflict-free LDS.128 of K and four broadcast LDS.128 of Q feed 16 FFMA, which keeps the kernel on
+// the FMA pipe instead of the shared-memory port (the one-row-per-warp version spent 31 us there).  The FMA order
+// inside a dot product (4 lanes of the float4, then (d0+d1)+(d2+d3)) and the softmax reduction order are fixed.
+// dynamic smem: (16*(D+nb) + 64*(D+4)) floats
 // ------------------------------------------------------------------------------------------------
+constexpr int kScoreRows = 16;
+constexpr int kScoreChunk = 64;
 __global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
                                                              float* __restrict__ scores, int nb, int D, float scale) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int DP = D + 4;
-  float* sq = sm + warp * D;                 // [8][D]
-  float* srow = sm + 8 * D + warp * nb;      // [8][nb]
-  float* sk = sm + 8 * (D + nb);             // [32][DP]
-  const int i = blockIdx.x * 8 + warp;
-  const bool active = i < nb;
+  const int d4n = D / 4;
+  float* sq = sm;                                  // [16][D]
+  float* srow = sm + kScoreRows * D;               // [16][nb]
+  float* sk = sm + kScoreRows * (D + nb);          // [64][DP]
+  const int i0 = blockIdx.x * kScoreRows;
   const int64_t bh = blockIdx.y;
-  if (active) {
-    const float* qrow = qm + (bh * nb + i) * D;
-    for (int d = lane; d < D; d += 32) sq[d] = qrow[d];
+  for (int e = threadIdx.x; e < kScoreRows * d4n; e += 256) {
+    const int r = e / d4n, c = e % d4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + r < nb) v = __ldg(reinterpret_cast<const float4*>(qm + (bh * nb + i0 + r) * D) + c);
+    reinterpret_cast<float4*>(sq + r * D)[c] = v;
   }
   const float* kb = km + bh * nb * D;
-  const int d4n = D / 4;
-  float mx = -INFINITY;
-  for (int j0 = 0; j0 < nb; j0 += 32) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * d4n; e += 256) {
+  constexpr int kPre = 8;  // 64 rows x D/4 float4 over 256 threads: D <= 128
+  float4 pre[kPre];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int e = threadIdx.x + u * 256;
       const int r = e / d4n, c = e % d4n;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < nb) v = __ldg(reinterpret_cast<const float4*>(kb + static_cast<int64_t>(j0 + r) * D) + c);
-      *reinterpret_cast<float4*>(sk + r * DP + 4 * c) = v;
+      pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < kScoreChunk * d4n && j0 + r < nb)
+        pre[u] = __ldg(reinterpret_cast<const float4*>(kb + static_cast<int64_t>(j0 + r) * D) + c);
+    }
+  };
+  fetch(0);
+  const int qg = threadIdx.x >> 6, kk = threadIdx.x & 63;
+  for (int j0 = 0; j0 < nb; j0 += kScoreChunk) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int e = threadIdx.x + u * 256;
+      if (e < kScoreChunk * d4n) *reinterpret_cast<float4*>(sk + (e / d4n) * DP + 4 * (e % d4n)) = pre[u];
     }
     __syncthreads();
-    if (active && j0 + lane < nb) {
-      const float4* kr = reinterpret_cast<const float4*>(sk + lane * DP);
-      const float4* qr = reinterpret_cast<const float4*>(sq);
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll 8
+    if (j0 + kScoreChunk < nb) fetch(j0 + kScoreChunk);
+    if (j0 + kk < nb) {
+      const float4* kr = reinterpret_cast<const float4*>(sk + kk * DP);
+      const float4* qr = reinterpret_cast<const float4*>(sq + 4 * qg * D);
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
+#pragma unroll 2
       for (int c = 0; c < d4n; ++c) {
         const float4 kv = kr[c];
-        const float4 qv = qr[c];
-        d0 = fmaf(qv.x, kv.x, d0);
-        d1 = fmaf(qv.y, kv.y, d1);
-        d2 = fmaf(qv.z, kv.z, d2);
-        d3 = fmaf(qv.w, kv.w, d3);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 qv = qr[a * d4n + c];
+          acc[a][0] = fmaf(qv.x, kv.x, acc[a][0]);
+          acc[a][1] = fmaf(qv.y, kv.y, acc[a][1]);
+          acc[a][2] = fmaf(qv.z, kv.z, acc[a][2]);
+          acc[a][3] = fmaf(qv.w, kv.w, acc[a][3]);
+        }
       }
-      const float dot = ((d0 + d1) + (d2 + d3)) * scale;
-      srow[j0 + lane] = dot;
-      mx = fmaxf(mx, dot);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        srow[(4 * qg + a) * nb + j0 + kk] = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) * scale;
     }
   }
-  if (!active) return;
-  __syncwarp();
+  __syncthreads();
+  // row softmax: two rows per warp
+  for (int rr = 0; rr < kScoreRows / 8; ++rr) {
+    const int r = warp * (kScoreRows / 8) + rr;
+    const int i = i0 + r;
+    if (i >= nb) break;
+    float* row = srow + r * nb;
+    float mx = -INFINITY;
+    for (int j = lane; j < nb; j += 32) mx = fmaxf(mx, row[j]);
 #pragma unroll
-  for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  float sum = 0.f;
-  for (int j = lane; j < nb; j += 32) {
-    const float e = expf(srow[j] - mx);
-    srow[j] = e;
-    sum += e;
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int j = lane; j < nb; j += 32) {
+      const float e = expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.0f / sum;
+    float* out = scores + (bh * nb + i) * nb;
+    for (int j = lane; j < nb; j += 32) out[j] = row[j] * inv;
   }
-#pragma unroll
-  for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float inv = 1.0f / sum;
-  float* out = scores + (bh * nb + i) * nb;
-  for (int j = lane; j < nb; j += 32) out[j] = srow[j] * inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,51 +429,54 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
   const int64_t bh = row / nq;
   const float* src = scores + row * nk;
 
-  float v[E];
-  int id[E];
+  // One 64-bit key per element: high word = the value's bits mapped to an order-preserving unsigned, low word =
+  // ~index.  "a before b" (value desc, index asc) is then a single unsigned compare ka > kb: 2 ISETP + 2 SEL per
+  // compare-exchange instead of three compares, predicate logic and two selects (the ALU pipe bounds this kernel).
+  // x + 0.0f folds -0.0 into +0.0, which torch.sort treats as equal.
+  uint64_t key[E];
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int p = lane * E + r;
-    v[r] = p < nk ? __ldg(src + p) : -INFINITY;              // padding sorts behind every real entry
-    id[r] = p;
+    const float x = p < nk ? __ldg(src + p) + 0.0f : -INFINITY;  // padding sorts behind every real entry
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t mono = b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+    key[r] = (static_cast<uint64_t>(mono) << 32) | static_cast<uint32_t>(~p);
   }
-  // "a comes before b" in the target order
-  auto before = [](float av, int ai, float bv, int bi) { return (av > bv) || (av == bv && ai < bi); };
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j >= 1; j >>= 1) {
       if (j >= E) {                                          // partner lives in lane ^ (j / E), same r
+        // p = lane*E + r with k, j multiples of E: direction and side depend on the lane only
+        const bool keep_if_first = ((lane * E) & k) == 0 == (((lane * E) & j) == 0);
 #pragma unroll
         for (int r = 0; r < E; ++r) {
-          const int p = lane * E + r;
-          const float ov = __shfl_xor_sync(0xffffffffu, v[r], j / E);
-          const int oi = __shfl_xor_sync(0xffffffffu, id[r], j / E);
-          const bool up = (p & k) == 0, lower = (p & j) == 0;
-          const bool mine_first = before(v[r], id[r], ov, oi);
-          const bool keep = mine_first == (up == lower);
-          v[r] = keep ? v[r] : ov;
-          id[r] = keep ? id[r] : oi;
+          const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], j / E);
+          const bool keep = (key[r] > ok) == keep_if_first;
+          key[r] = keep ? key[r] : ok;
         }
       } else {                                               // partner is register r ^ j of the same lane
 #pragma unroll
         for (int r = 0; r < E; ++r) {
           if ((r & j) == 0) {
             const int r2 = r | j;
-            const int p = lane * E + r;
-            const bool up = (p & k) == 0;
-            const bool first = before(v[r], id[r], v[r2], id[r2]);
-            const bool swap = first != up;                   // lower slot must hold the "first" element iff up
-            const float tv = v[r];
-            const int ti = id[r];
-            v[r] = swap ? v[r2] : tv;
-            id[r] = swap ? id[r2] : ti;
-            v[r2] = swap ? tv : v[r2];
-            id[r2] = swap ? ti : id[r2];
+            const bool up = ((lane * E + r) & k) == 0;
+            const bool swap = (key[r] > key[r2]) != up;      // lower slot must hold the "first" element iff up
+            const uint64_t t = key[r];
+            key[r] = swap ? key[r2] : t;
+            key[r2] = swap ? t : key[r2];
           }
         }
       }
     }
+  }
+  float v[E];
+  int id[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const uint32_t mono = static_cast<uint32_t>(key[r] >> 32);
+    v[r] = __uint_as_float(mono ^ ((mono >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+    id[r] = static_cast<int>(~static_cast<uint32_t>(key[r]));
   }
 #pragma unroll
   for (int r = 0; r < E; ++r) {
@@ -652,13 +693,13 @@ extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mea
                                          int64_t nb, int64_t D, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BLADE_REQUIRE(q_mean && k_mean && scores, BLADE_ERR_ARG, "null pointer");
-  BLADE_REQUIRE(D % 4 == 0 && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
-  const size_t smem = (8 * (D + nb) + 32 * (D + 4)) * sizeof(float);
+  BLADE_REQUIRE(D % 4 == 0 && D <= 128 && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
+  const size_t smem = (kScoreRows * (D + nb) + kScoreChunk * (D + 4)) * sizeof(float);
   BLADE_REQUIRE(smem <= 200 * 1024, BLADE_ERR_SHAPE, "nb too large for score kernel");
   if (smem > 48 * 1024)
     BLADE_CUDA_OK(cudaFuncSetAttribute(score_meanpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StageTimer timer(1, stream);
-  dim3 grid(static_cast<unsigned>(ceil_div(nb, 8)), static_cast<unsigned>(B * H));
+  dim3 grid(static_cast<unsigned>(ceil_div(nb, kScoreRows)), static_cast<unsigned>(B * H));
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   score_meanpool_kernel<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, (int)D, scale);
   BLADE_CUDA_OK(cudaGetLastError());
