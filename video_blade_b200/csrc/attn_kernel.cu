@@ -57,10 +57,6 @@ constexpr int kSoftmaxThreads = 128;
 constexpr float kRescaleThresh = 8.0f;  // log2 units
 constexpr int kRegsSoftmax = 224;      // setmaxnreg split: 8 softmax warps x 224 + 4 other warps x 56 = 64512
 constexpr int kRegsOther = 56;
-#ifndef BLADE_POLY_MASK
-#define BLADE_POLY_MASK 0x00  // bit i set: element i of every 8 uses ex2_poly.  Measured on B200 (profiles/README.md): 0x00 1.22 ms, 0x22 1.25, 0x2A 1.32, 0xAA 1.37 -> off
-#endif
-constexpr unsigned kPolyMask = BLADE_POLY_MASK;
 constexpr int kMaxListSmem = 128;       // per-stream block ids cached in smem by the producer (longer lists: __ldg)
 constexpr float kLn2 = 0.69314718055994530942f;
 
@@ -116,6 +112,14 @@ __device__ __forceinline__ uint32_t pack_t(float lo, float hi) {
   return IS_BF16 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi);
 }
 template <bool IS_BF16>
+__device__ __forceinline__ uint32_t mul_t(uint32_t a, uint32_t b) {
+  return IS_BF16 ? mul_bf16x2(a, b) : mul_f16x2(a, b);
+}
+template <bool IS_BF16>
+__device__ __forceinline__ uint32_t add_t(uint32_t a, uint32_t b) {
+  return IS_BF16 ? add_bf16x2(a, b) : add_f16x2(a, b);
+}
+template <bool IS_BF16>
 __device__ __forceinline__ float2 unpack_t(uint32_t w) {
   if (IS_BF16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
   return __half22float2(*reinterpret_cast<const __half2*>(&w));
@@ -128,6 +132,31 @@ __device__ __forceinline__ uint32_t kmajor_koff(int k) {
   return static_cast<uint32_t>((k >> 2) * (kBlockN * 128 / 16) + (k & 3) * 2);
 }
 
+__device__ __forceinline__ uint4 shfl_xor_u4(const uint4& v, int mask) {
+  return make_uint4(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask),
+                    __shfl_xor_sync(0xffffffffu, v.z, mask), __shfl_xor_sync(0xffffffffu, v.w, mask));
+}
+// 4x4 transpose of 16-byte elements inside every group of 4 consecutive lanes.  In: a[u] = part u of this lane's
+// row.  Out: a[j] = part (lane & 3) of the row of lane (lane & ~3) + j.  Two butterfly rounds, 16 SHFL.
+// The epilogue uses it so that a warp-wide 16-byte store covers 8 rows x 64 contiguous bytes instead of 32 rows x
+// 16 bytes: the row-per-lane store pattern cost ~2 000 L2 requests (5-9 k cycles) per tile.
+__device__ __forceinline__ void transpose4x4(uint4 (&a)[4], int lane) {
+  const bool hi = lane & 2, lo = lane & 1;
+  // round 1 (xor 2): afterwards the lane holds parts {2hi, 2hi+1} of rows {me & ~2, me | 2}
+  const uint4 s0 = hi ? a[0] : a[2], s1 = hi ? a[1] : a[3];
+  const uint4 r0 = shfl_xor_u4(s0, 2), r1 = shfl_xor_u4(s1, 2);
+  // t[row bit1][part bit0]
+  const uint4 t00 = hi ? r0 : a[0], t01 = hi ? r1 : a[1];
+  const uint4 t10 = hi ? a[2] : r0, t11 = hi ? a[3] : r1;
+  // round 2 (xor 1): keep part 2hi+lo, trade the other part for the neighbour row's
+  const uint4 q0 = lo ? t00 : t01, q1 = lo ? t10 : t11;
+  const uint4 x0 = shfl_xor_u4(q0, 1), x1 = shfl_xor_u4(q1, 1);
+  a[0] = lo ? x0 : t00;
+  a[1] = lo ? t01 : x0;
+  a[2] = lo ? x1 : t10;
+  a[3] = lo ? t11 : x1;
+}
+
 // One work item as the three roles see it: per stream t its query tile, how many pooled tiles it runs first,
 // and which slice [off, off + ns) of the row's block list it owns.
 struct Item {
@@ -135,7 +164,26 @@ struct Item {
   int qb[2], pt[2], off[2], ns[2];
   bool merge;  // solo item with work on both streams: warpgroup 0 folds stream 1's accumulator into its own
 };
-__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+// The per-row block counts are the only global-memory input of the decode; every role requests the NEXT item's
+// counts at the top of the current item (item_counts) and turns them into an Item one iteration later (make_item),
+// so no role stalls on a dependent load at an item boundary.
+__device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& c0, int& c1) {
+  c0 = c1 = 0;
+  if (item >= p.num_items) return;
+  if (item < p.num_pair_items) {
+    const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
+    const int32_t* row = p.cnt + static_cast<int64_t>(bh) * p.nq + 2 * pair;
+    c0 = __ldg(row);
+    if (2 * pair + 1 < p.nq) c1 = __ldg(row + 1);
+  } else {
+    const int s = item - p.num_pair_items;
+    const int pid = p.num_pair_items + (s >> 1);
+    const int bh = pid / p.pairs_per_head;
+    const int qb = 2 * (pid % p.pairs_per_head) + (s & 1);
+    if (qb < p.nq) c0 = c1 = __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
+  }
+}
+__device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0, int c1) {
   Item it;
   const int npt = p.n_pool_tiles;
   if (item < p.num_pair_items) {
@@ -149,7 +197,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
       it.qb[t] = qb;
       it.pt[t] = valid ? npt : 0;
       it.off[t] = 0;
-      it.ns[t] = valid ? __ldg(p.cnt + static_cast<int64_t>(it.bh) * p.nq + qb) : 0;
+      it.ns[t] = valid ? (t ? c1 : c0) : 0;
     }
   } else {
     const int s = item - p.num_pair_items;
@@ -157,7 +205,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
     it.bh = pid / p.pairs_per_head;
     const int qb = 2 * (pid % p.pairs_per_head) + (s & 1);
     const bool valid = qb < p.nq;
-    const int c = valid ? __ldg(p.cnt + static_cast<int64_t>(it.bh) * p.nq + qb) : 0;
+    const int c = valid ? c0 : 0;
     // balance pooled + a  against  c - a tiles
     int a = c;
     if (c >= 2) {
@@ -177,7 +225,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
 }
 
 // ================================================================================================
-template <int D, bool IS_BF16>
+template <int D, bool IS_BF16, bool POOLED>
 __global__ void __launch_bounds__(kThreads, 1)
 asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
@@ -235,8 +283,11 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     setmaxnreg_dec<kRegsOther>();
     uint32_t slot = 0, ph = 0;  // ring position / phase of the NEXT load
     uint32_t q_it[2] = {0, 0};
+    int c0n, c1n;
+    item_counts(p, blockIdx.x, c0n, c1n);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+      const Item it = make_item(p, item, c0n, c1n);
+      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
       const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
       int ns[2], nt[2];
@@ -314,8 +365,11 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t g[2] = {0, 0};
     uint32_t q_it[2] = {0, 0};
     const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+    int c0n, c1n;
+    item_counts(p, blockIdx.x, c0n, c1n);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+      const Item it = make_item(p, item, c0n, c1n);
+      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
       const int nt[2] = {it.pt[0] + it.ns[0], it.pt[1] + it.ns[1]};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -406,8 +460,11 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int pool_tail = p.n_pool - (npt - 1) * kBlockN;
     const int seq_tail = p.Sk - (p.nk - 1) * kBlockN;  // valid keys in the last key block
 
+    int c0n, c1n;
+    item_counts(p, blockIdx.x, c0n, c1n);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+      const Item it = make_item(p, item, c0n, c1n);
+      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
       const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
       const int qb = t ? it.qb[1] : it.qb[0];  // selects, not indexing: keeps Item in registers
@@ -421,6 +478,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int last_kb = ns > 0 ? (__ldg(my_list + ns - 1) & 0x0FFFFFFF) : -1;
       const int sparse_tail = (last_kb == p.nk - 1) ? seq_tail : kBlockN;
       float lse2 = 0.f;
+      if (wq == 0 && sparse_tail > 0) TRACE(t, 7, g);  // item decoded (both dependent loads done)
 
       for (int phase = (my_pt ? 0 : 1); phase < 2; ++phase) {
         const int ntile = phase == 0 ? my_pt : ns;
@@ -516,35 +574,22 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lane == 0) mbar_arrive(&mz->p_hi[t]);
           if (wq == 0) TRACE(t, 4, g);
         }
-        // ---- phase finalisation: the last PV of this phase has to retire first
-        mbar_wait(&mz->o_full[t], (g - 1) & 1);
-        tc_fence_after();
+        // ---- phase finalisation: the last PV of the phase has to retire first (o_full)
         if (it.merge && t == 1) {
           // solo item, second half of the list: hand (m, l) to warpgroup 0, which reads O1 from TMEM itself
+          mbar_wait(&mz->o_full[t], (g - 1) & 1);
           mz->ml[row_in_tile] = make_float2(m, l);
           tc_fence_before();
           named_bar_arrive<1, 2 * kSoftmaxThreads>();
           named_bar_sync<2, 2 * kSoftmaxThreads>();  // O1 has been read: the next item may overwrite it
           continue;
         }
-        float w1 = 0.f;  // weight of stream 1's accumulator (solo items)
-        float a0 = 1.f;
-        if (it.merge && phase == 1) {
-          named_bar_sync<1, 2 * kSoftmaxThreads>();
-          tc_fence_after();
-          const float2 ml1 = mz->ml[row_in_tile];
-          const float mm = fmaxf(m, ml1.x);
-          a0 = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
-          w1 = (ml1.x == -INFINITY) ? 0.f : ex2_approx(ml1.x - mm);
-          l = a0 * l + w1 * ml1.y;
-          m = mm;
-        }
-        const float inv_l = 1.0f / l;
-        const float lse = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
-        const float w0 = a0 * inv_l;
-        w1 *= inv_l;
         if (phase == 0) {
-          lse2 = lse;
+          // pooled branch done: normalise, round to the tensor dtype and park it until the sparse branch is done
+          mbar_wait(&mz->o_full[t], (g - 1) & 1);
+          tc_fence_after();
+          const float inv_l = 1.0f / l;
+          lse2 = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
             uint32_t o[32];
@@ -561,32 +606,72 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         } else {
+          // Everything the epilogue needs from global memory (the parked pooled-branch result, 16 bytes per 8
+          // columns, and the inverse-permutation row) is requested BEFORE waiting for the last PV: one overlapped L2
+          // round trip instead of a dependent one per 8 columns (which cost ~10 us per item).
           const int r = qb * kBlockM + row_in_tile;
           const bool store = r < p.S;
-          float alpha = 1.f, oma = 0.f;
-          if (npt) {
-            if (p.exact_merge) {
-              // W:351-370 op by op, every intermediate rounded to the tensor dtype (lse already is, W:309)
-              const float a = round_t<IS_BF16>(lse);
-              const float b2 = round_t<IS_BF16>(round_t<IS_BF16>(lse2) + p.log_gap_r);
-              const float mxw = fmaxf(a, b2);
-              const float e1 = round_t<IS_BF16>(expf(round_t<IS_BF16>(a - mxw)));
-              const float e2 = round_t<IS_BF16>(expf(round_t<IS_BF16>(b2 - mxw)));
-              alpha = round_t<IS_BF16>(e1 / round_t<IS_BF16>(e1 + e2));
-              oma = round_t<IS_BF16>(1.0f - alpha);
-            } else {
-              alpha = 1.0f / (1.0f + p.gap * expf(lse2 - lse));
-              oma = 1.0f - alpha;
-            }
+          uint4 parked[D / 8];
+          if (POOLED) {  // compile-time: a runtime predicate here sends the array through local memory
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) parked[i] = park[i * kBlockM + row_in_tile];
           }
           int dst = r;
           if (store && p.dst_row) dst = __ldg(p.dst_row + r);
-          uint16_t* orow = p.out + b * p.out_sb + h * p.out_sh + static_cast<int64_t>(dst) * p.out_ss;
+          // (m, l) are final once the last tile's exponentials are summed, i.e. BEFORE its PV retires: the merge
+          // weights and the row pointers are computed under the o_full wait (solo items redo them after the fold)
+          float w0, w1 = 0.f, lse, alpha = 1.f, oma = 0.f;
+          auto weights = [&](float a0) {
+            const float inv_l = 1.0f / l;
+            lse = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
+            w0 = a0 * inv_l;
+            w1 *= inv_l;
+            if (POOLED) {
+              if (p.exact_merge) {
+                // W:351-370 op by op, every intermediate rounded to the tensor dtype (lse already is, W:309)
+                const float a = round_t<IS_BF16>(lse);
+                const float b2 = round_t<IS_BF16>(round_t<IS_BF16>(lse2) + p.log_gap_r);
+                const float mxw = fmaxf(a, b2);
+                const float e1 = round_t<IS_BF16>(expf(round_t<IS_BF16>(a - mxw)));
+                const float e2 = round_t<IS_BF16>(expf(round_t<IS_BF16>(b2 - mxw)));
+                alpha = round_t<IS_BF16>(e1 / round_t<IS_BF16>(e1 + e2));
+                oma = round_t<IS_BF16>(1.0f - alpha);
+              } else {
+                alpha = 1.0f / (1.0f + p.gap * expf(lse2 - lse));
+                oma = 1.0f - alpha;
+              }
+            }
+          };
+          if (!it.merge) weights(1.f);
+          uint16_t* orow = store ? p.out + b * p.out_sb + h * p.out_sh + static_cast<int64_t>(dst) * p.out_ss : nullptr;
+          // output row pointers of the 4 lanes of my group (null = row beyond S): after the 4x4 transpose lane L
+          // stores part L & 3 of each of them
+          uint16_t* orow_j[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            orow_j[j] = reinterpret_cast<uint16_t*>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(orow), (lane & ~3) + j));
+          mbar_wait(&mz->o_full[t], (g - 1) & 1);
+          tc_fence_after();
+          if (wq == 0) TRACE(t, 5, g - 1);
+          uint32_t ob[2][32];  // the accumulator chunks are loaded one ahead of the arithmetic
+          tmem_ld32(tO, ob[0]);
+          if (it.merge) {
+            named_bar_sync<1, 2 * kSoftmaxThreads>();
+            tc_fence_after();
+            const float2 ml1 = mz->ml[row_in_tile];
+            const float mm = fmaxf(m, ml1.x);
+            const float a0 = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
+            w1 = (ml1.x == -INFINITY) ? 0.f : ex2_approx(ml1.x - mm);
+            l = a0 * l + w1 * ml1.y;
+            m = mm;
+            weights(a0);
+          }
+          const uint32_t alpha2 = pack_t<IS_BF16>(alpha, alpha), oma2 = pack_t<IS_BF16>(oma, oma);
           if (store && p.lse) p.lse[static_cast<int64_t>(bh) * p.S + r] = lse;
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + c * 32, o);
+            uint32_t(&o)[32] = ob[c & 1];
             if (it.merge) {
               uint32_t o1[32];
               tmem_ld32(tO + D + c * 32, o1);  // stream 1's accumulator: same lanes, next D columns
@@ -599,42 +684,44 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * w0);
             }
+            if (c + 1 < D / 32) tmem_ld32(tO + (c + 1) * 32, ob[(c + 1) & 1]);
+            uint4 wq4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float f[8];
+              uint32_t wv[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * u + i]);
-              if (npt) {
-                const uint4 w2 = park[(c * 4 + u) * kBlockM + row_in_tile];
-                const uint32_t ww[4] = {w2.x, w2.y, w2.z, w2.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 o2 = unpack_t<IS_BF16>(ww[i]);
+              for (int i = 0; i < 4; ++i) {
+                const float f0 = __uint_as_float(o[8 * u + 2 * i]), f1 = __uint_as_float(o[8 * u + 2 * i + 1]);
+                if (!POOLED) {
+                  wv[i] = pack_t<IS_BF16>(f0, f1);
+                } else {
+                  const uint4 w2 = parked[c * 4 + u];
+                  const uint32_t pw = i == 0 ? w2.x : (i == 1 ? w2.y : (i == 2 ? w2.z : w2.w));
                   if (p.exact_merge) {
-                    const float x0 = round_t<IS_BF16>(round_t<IS_BF16>(f[2 * i]) * alpha);
-                    const float x1 = round_t<IS_BF16>(round_t<IS_BF16>(f[2 * i + 1]) * alpha);
-                    const float y0 = round_t<IS_BF16>(o2.x * oma);
-                    const float y1 = round_t<IS_BF16>(o2.y * oma);
-                    f[2 * i] = x0 + y0;
-                    f[2 * i + 1] = x1 + y1;
+                    // out1 * alpha + out2 * (1 - alpha) as three tensor-dtype ops (W:368-370): packed native
+                    // 16-bit multiplies / add, each rounding once like the element-wise torch ops they mirror
+                    const uint32_t x = mul_t<IS_BF16>(pack_t<IS_BF16>(f0, f1), alpha2);
+                    const uint32_t y = mul_t<IS_BF16>(pw, oma2);
+                    wv[i] = add_t<IS_BF16>(x, y);
                   } else {
-                    f[2 * i] = f[2 * i] * alpha + o2.x * oma;
-                    f[2 * i + 1] = f[2 * i + 1] * alpha + o2.y * oma;
+                    const float2 o2 = unpack_t<IS_BF16>(pw);
+                    wv[i] = pack_t<IS_BF16>(f0 * alpha + o2.x * oma, f1 * alpha + o2.y * oma);
                   }
                 }
               }
-              uint4 w;
-              w.x = pack_t<IS_BF16>(f[0], f[1]);
-              w.y = pack_t<IS_BF16>(f[2], f[3]);
-              w.z = pack_t<IS_BF16>(f[4], f[5]);
-              w.w = pack_t<IS_BF16>(f[6], f[7]);
-              if (store) reinterpret_cast<uint4*>(orow)[c * 4 + u] = w;
+              wq4[u] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             }
+            transpose4x4(wq4, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (orow_j[j]) reinterpret_cast<uint4*>(orow_j[j])[c * 4 + (lane & 3)] = wq4[j];
+            if (wq == 0 && c < 4) TRACE(2 + t, 3 + c, g - 1);
           }
           if (it.merge) {
             tc_fence_before();
             named_bar_arrive<2, 2 * kSoftmaxThreads>();
           }
+          if (wq == 0) TRACE(t, 6, g - 1);
         }
         // O_t / S_t are handed back implicitly: the next PV of this stream waits for our next p_full.
         tc_fence_before();
@@ -849,7 +936,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   StageTimer timer(3, stream);
 #define LAUNCH_ATTN(DD, BF)                                                                                     \
   do {                                                                                                          \
-    auto kern = asa_attn_kernel<DD, BF>;                                                                        \
+    auto kern = pooled ? asa_attn_kernel<DD, BF, true> : asa_attn_kernel<DD, BF, false>;                        \
     BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<DD>::kTotal)); \
     kern<<<grid, kThreads, SmemLayout<DD>::kTotal, stream>>>(tmQ, tmK, tmV, tmKp, tmVp, p);                      \
   } while (0)
