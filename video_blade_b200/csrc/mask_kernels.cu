@@ -236,12 +236,13 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreRows = 16;
 constexpr int kScoreChunk = 64;
-__global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
-                                                             float* __restrict__ scores, int nb, int D, float scale) {
+template <int D>
+__global__ void __launch_bounds__(256, 3) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
+                                                             float* __restrict__ scores, int nb, float scale) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int DP = D + 4;
-  const int d4n = D / 4;
+  constexpr int DP = D + 4;
+  constexpr int d4n = D / 4;
   float* sq = sm;                                  // [16][D]
   float* srow = sm + kScoreRows * D;               // [16][nb]
   float* sk = sm + kScoreRows * (D + nb);          // [64][DP]
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256) score_meanpool_kernel(const float* __rest
     reinterpret_cast<float4*>(sq + r * D)[c] = v;
   }
   const float* kb = km + bh * nb * D;
-  constexpr int kPre = 8;  // 64 rows x D/4 float4 over 256 threads: D <= 128
+  constexpr int kPre = kScoreChunk * d4n / 256;  // 64 rows x D/4 float4 over 256 threads
   float4 pre[kPre];
   auto fetch = [&](int j0) {
 #pragma unroll
@@ -693,15 +694,16 @@ extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mea
                                          int64_t nb, int64_t D, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BLADE_REQUIRE(q_mean && k_mean && scores, BLADE_ERR_ARG, "null pointer");
-  BLADE_REQUIRE(D % 4 == 0 && D <= 128 && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
+  BLADE_REQUIRE((D == 64 || D == 128) && nb >= 1 && nb <= 4096, BLADE_ERR_SHAPE, "bad nb/D");
   const size_t smem = (kScoreRows * (D + nb) + kScoreChunk * (D + 4)) * sizeof(float);
   BLADE_REQUIRE(smem <= 200 * 1024, BLADE_ERR_SHAPE, "nb too large for score kernel");
-  if (smem > 48 * 1024)
-    BLADE_CUDA_OK(cudaFuncSetAttribute(score_meanpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StageTimer timer(1, stream);
   dim3 grid(static_cast<unsigned>(ceil_div(nb, kScoreRows)), static_cast<unsigned>(B * H));
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
-  score_meanpool_kernel<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, (int)D, scale);
+  auto kern = D == 128 ? score_meanpool_kernel<128> : score_meanpool_kernel<64>;
+  if (smem > 48 * 1024)
+    BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, scale);
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
 }
