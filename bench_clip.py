@@ -58,7 +58,6 @@ def main():
             return torch.nn.functional.scaled_dot_product_attention(q, k, v)
     g = torch.Generator(device="cpu").manual_seed(1)
     if a.model == "cog":
-        assert world == 1, "the CogVideoX scaffold is single-GPU (its Ulysses processor is not written)"
         from video_blade_b200 import cogvideo_blocksparseattn as Cg
         from video_blade_b200.dit import CogLikeDiT
         from video_blade_b200.modify_cogvideo import set_block_sparse_attn_cogvideox
@@ -69,6 +68,7 @@ def main():
             model = CogLikeDiT(layers=layers).to(torch.bfloat16).eval()
         blocks = model.transformer_blocks
         inner = set_block_sparse_attn_cogvideox(model)
+        model.set_sequence_parallel(group)
         noise = torch.randn(1, 13, 16, 60, 90, generator=g).to(dev, torch.bfloat16)
         prompt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
         negative = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)

@@ -84,3 +84,54 @@ def _worker_fused(rank, world, degree, port, S, H, D):
 def test_ulysses_fused_scatter_layout_gloo(world, degree):
     port = _free_port()
     mp.spawn(_worker_fused, args=(world, degree, port, 24, 12, 8), nprocs=world, join=True)
+
+
+# ------------------------------------------------------------------ CogVideoX scaffold, sequence-parallel blocks
+class _DenseInner(torch.nn.Module):
+    """Stand-in for the ASA module on CPU: plain attention, reading q/k/v out of the packed Ulysses receive buffer
+    through the virtual-row table exactly like prep_block_kernel does on the GPU."""
+
+    def forward(self, q, k, v, virtual_rows=None, rotary=None):
+        if virtual_rows is not None:
+            _, Hl, S, D = q.shape
+            rows = virtual_rows.long()
+
+            def gather(x):
+                flat = x.as_strided((int(rows.max()) + 1, Hl, D), (Hl * D, D, 1), x.storage_offset())
+                return flat[rows].permute(1, 0, 2)[None]                        # [1,Hl,S,D]
+            q, k, v = gather(q), gather(k), gather(v)
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v)
+
+
+def _worker_cog(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from video_blade_b200.dit import CogLikeDiT
+        from video_blade_b200.modify_cogvideo import SageAttnCogVideoXAttnProcessor
+        from video_blade_b200.ulysses import UlyssesGroup
+        torch.manual_seed(0)
+        model = CogLikeDiT(dim=64, heads=4, layers=2, text_dim=24, in_ch=4, patch=2, temb_dim=32).eval()
+        inner = _DenseInner()
+        for i, blk in enumerate(model.transformer_blocks):
+            blk.attn1.inner_attention = inner
+            blk.attn1.set_processor(SageAttnCogVideoXAttnProcessor(i, fuse_rope=False))
+        g = torch.Generator().manual_seed(3)
+        lat = torch.randn(2, 2, 4, 8, 8, generator=g)            # 2 x 4 x 4 = 32 video tokens
+        txt = torch.randn(2, 6, 24, generator=g)                 # 6 text tokens -> 38 = 2 x 19
+        t = torch.tensor([300.0, 700.0])
+        with torch.no_grad():
+            ref = model(lat, t, txt)
+            model.set_sequence_parallel(UlyssesGroup(world, rank, world))
+            got = model(lat, t, txt)
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), float((got - ref).abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cog_scaffold_sequence_parallel_matches_single_rank_gloo():
+    """[text ; video] sharded over 2 ranks: per-token text/video modulation, identity rotary rows for text, the
+    fused q/k/v exchange and the final all-gather reproduce the unsharded forward."""
+    mp.spawn(_worker_cog, args=(2, _free_port()), nprocs=2, join=True)

@@ -54,6 +54,34 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
         return attn.to_out[1](attn.to_out[0](o))
 
 
+class UlyssesCogAttnProcessor:
+    """SageAttnCogVideoXAttnProcessor (MC:11-76) on a token shard of the concatenated [text ; video] sequence, with
+    the Ulysses exchange around `inner_attention`.  `rope_local` = (cos, sin) [S/P, D] for my tokens, identity rows
+    for text tokens (MC:59-64 rotates the video part only)."""
+
+    def __init__(self, group: UlyssesGroup):
+        self.group = group
+
+    def __call__(self, attn, hidden_states, rope_local):
+        from .modify_cogvideo import apply_rotary_emb as cog_rope
+        B, Sl, _ = hidden_states.shape
+        q = attn.to_q(hidden_states).view(B, Sl, attn.heads, -1)
+        k = attn.to_k(hidden_states).view(B, Sl, attn.heads, -1)
+        v = attn.to_v(hidden_states).view(B, Sl, attn.heads, -1)
+        q = attn.norm_q(q).to(v.dtype)                                                 # LayerNorm per head (MC:54-57)
+        k = attn.norm_k(k).to(v.dtype)
+        q = cog_rope(q.transpose(1, 2), rope_local).transpose(1, 2)
+        k = cog_rope(k.transpose(1, 2), rope_local).transpose(1, 2)
+        outs = []
+        for b in range(B):                                                             # exchange is per sequence
+            gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
+                                                                     v[b:b + 1].contiguous())
+            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow)                    # [1, H/P, S, D], text first
+            outs.append(self.group.gather_heads(o.transpose(1, 2)))                    # [1, S/P, H, D]
+        o = torch.cat(outs, 0).flatten(2, 3).type_as(hidden_states)
+        return attn.to_out[1](attn.to_out[0](o))
+
+
 class CrossAttention(nn.Module):
     def __init__(self, dim, heads):
         super().__init__()
@@ -284,6 +312,38 @@ class CogLikeDiT(nn.Module):
         self.norm_out = nn.LayerNorm(dim, eps=1e-5, elementwise_affine=False)
         self.proj_out = nn.Linear(dim, in_ch * patch * patch)
         self._rope = {}
+        self.group: Optional[UlyssesGroup] = None
+
+    def set_sequence_parallel(self, group: Optional[UlyssesGroup]):
+        """Ulysses degree P: every rank keeps S/P tokens of the concatenated [text ; video] sequence."""
+        self.group = group
+
+    def _blocks_sequence_parallel(self, x, txt, temb, rope):
+        """The transformer blocks on my shard of [text ; video]; returns the full-length video / text streams."""
+        import torch.distributed as dist
+        g = self.group
+        T, S = txt.shape[1], txt.shape[1] + x.shape[1]
+        assert S % g.P == 0, f"{S} tokens do not split over Ulysses degree {g.P}"
+        Sl = S // g.P
+        sl = slice(g.rank_in_group * Sl, (g.rank_in_group + 1) * Sl)
+        hs = torch.cat([txt, x], dim=1)[:, sl]
+        is_text = (torch.arange(S, device=x.device)[sl] < T)[None, :, None]
+        cos, sin = rope                                                            # [Sv, D] video rows
+        D = cos.shape[-1]
+        cos_f = torch.cat([torch.ones(T, D, device=cos.device), cos])[sl]         # identity for text rows
+        sin_f = torch.cat([torch.zeros(T, D, device=sin.device), sin])[sl]
+        proc = UlyssesCogAttnProcessor(g)
+        for blk in self.transformer_blocks:
+            for norm, fn in ((blk.norm1, lambda h, a=blk.attn1: proc(a, h, (cos_f, sin_f))), (blk.norm2, blk.ff)):
+                sh, sc, gt, tsh, tsc, tg = norm.linear(F.silu(temb)).chunk(6, dim=1)
+                shift = torch.where(is_text, tsh[:, None], sh[:, None])
+                scale = torch.where(is_text, tsc[:, None], sc[:, None])
+                gate = torch.where(is_text, tg[:, None], gt[:, None])
+                hs = hs + gate * fn(norm.norm(hs) * (1 + scale) + shift)
+        parts = [torch.empty_like(hs) for _ in range(g.P)]
+        dist.all_gather(parts, hs.contiguous(), group=g.group)
+        full = torch.cat(parts, dim=1)
+        return full[:, T:], full[:, :T]
 
     def forward(self, hidden_states, timestep, encoder_hidden_states):
         """hidden_states [B,F,C,H,W] latents (CogVideoX layout); encoder_hidden_states [B,226,4096]."""
@@ -300,8 +360,11 @@ class CogLikeDiT(nn.Module):
         if key not in self._rope:
             self._rope[key] = rope_cos_sin(Fr, H // p, W // p, self.dim // self.heads, device=x.device)
         rope = self._rope[key]
-        for blk in self.transformer_blocks:
-            x, txt = blk(x, txt, temb, rope)
+        if self.group is not None and self.group.P > 1:
+            x, txt = self._blocks_sequence_parallel(x, txt, temb, rope)
+        else:
+            for blk in self.transformer_blocks:
+                x, txt = blk(x, txt, temb, rope)
         x = self.norm_final(x)
         sh, sc = self.norm_out_linear(F.silu(temb)).chunk(2, dim=1)
         x = self.proj_out(self.norm_out(x) * (1 + sc[:, None]) + sh[:, None])
