@@ -92,6 +92,10 @@ int blade_gilbert_tables(int32_t width, int32_t height, int32_t depth,
 
 /* ---- workspace ------------------------------------------------------------------------------ */
 size_t blade_asa_workspace_bytes(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg);
+/* workspace of the stand-alone attention entry points below (item counter + one parked pooled-branch tile per SM
+ * and stream; 16-byte aligned).  blade_block_sparse_attn*_fwd accept NULL: items are then assigned round-robin
+ * instead of being claimed from the counter. */
+size_t blade_attn_workspace_bytes(int64_t D);
 
 /* ---- prep: gather into curve order + block means + gap-pooled K/V ---------------------------
  * src_row (device int32[S], may be NULL = identity): row of q/k/v that lands at output row r

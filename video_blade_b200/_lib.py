@@ -34,6 +34,7 @@ SYMBOLS = [
     "blade_mask_to_index", "blade_block_sparse_attn_fwd", "blade_asa_attn_fwd", "blade_asa_forward",
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
     "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
+    "blade_attn_workspace_bytes",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -57,6 +58,8 @@ def load() -> C.CDLL:
     lib.blade_gilbert_tables.argtypes = [i32, i32, i32, vp, vp]
     lib.blade_asa_workspace_bytes.argtypes = [i64, i64, i64, i64, CFG]
     lib.blade_asa_workspace_bytes.restype = C.c_size_t
+    lib.blade_attn_workspace_bytes.argtypes = [i64]
+    lib.blade_attn_workspace_bytes.restype = C.c_size_t
     lib.blade_asa_prep.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.blade_asa_prep_rope.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp]
     lib.blade_asa_scores_meanpool.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]

@@ -265,8 +265,7 @@ class AsaEngine:
         return out, cnt
 
     def _park(self, device, D):
-        sms = torch.cuda.get_device_properties(device).multi_processor_count
-        return self.workspace(device, sms * 2 * (D // 8) * 128 * 16)
+        return self.workspace(device, int(self.lib.blade_attn_workspace_bytes(D)))
 
     def block_sparse_attn(self, q, k, v, idx, cnt, out=None, dst_row=None, want_lse=True, sub64=False):
         """block_sparse_attn(q,k,v,block_mask) (W:278-309) on an index list; returns (out, lse fp32 [B,H,S])."""

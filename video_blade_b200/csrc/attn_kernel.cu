@@ -17,6 +17,10 @@
 //                    128-column S row, online softmax in registers with lazy O rescale (threshold 2^8),
 //                    tcgen05.st of P, final normalise + merge + (inverse-Gilbert) row store;
 //   * TMEM map (512 columns): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [256+D,256+2D).
+//   * scheduling: items are claimed from a global atomic counter by the producer warp, which publishes
+//     (item, block counts) through a 4-deep shared-memory queue to the issuer and the softmax warps -- rows keep
+//     different numbers of blocks on real inputs, and a static round-robin lost 10-13 % there
+//     (tools/imbalance_probe.py).  Without a workspace the same queue is fed with the static sequence.
 //   * tail round: when the last round of pair items would occupy at most half of the CTAs, those pairs are
 //     issued as "solo" items instead -- ONE query tile per CTA whose KV sequence is split between the two
 //     streams (stream 0: pooled tiles + first part of the list, stream 1: the rest); warpgroup 0 reads both
@@ -59,6 +63,8 @@ constexpr int kRegsSoftmax = 224;      // setmaxnreg split: 8 softmax warps x 22
 constexpr int kRegsOther = 56;
 constexpr int kMaxListSmem = 128;       // per-stream block ids cached in smem by the producer (longer lists: __ldg)
 constexpr float kLn2 = 0.69314718055994530942f;
+constexpr int kItemSlots = 4;          // depth of the per-CTA item queue
+constexpr int kSchedBytes = 256;       // head of the attention workspace: the global item counter
 
 template <int D>
 struct SmemLayout {
@@ -79,6 +85,9 @@ struct Misc {
   uint32_t pad;
   uint16_t list[2][kMaxListSmem];
   float2 ml[kBlockM];  // solo items: stream 1's (m, l) per query row, handed to warpgroup 0
+  // work queue: the producer warp claims items (atomic counter) and publishes (item, cnt0, cnt1) here
+  int4 items[kItemSlots];
+  uint64_t item_full[kItemSlots], item_empty[kItemSlots];
 };
 static_assert(sizeof(Misc) <= 2048, "misc smem region overflow");
 
@@ -95,6 +104,8 @@ struct AttnParams {
   int n_pool, n_pool_tiles;
   int num_items, pairs_per_head;
   int num_pair_items;      // items [0, num_pair_items) are tile pairs, the rest are solo tiles (two per pair id)
+  int num_solo_pairs;      // pair ids [0, num_solo_pairs) run as solo tiles
+  int* sched;              // global item counter (zeroed before the launch); null = static round-robin
   float scale_log2;        // softmax_scale * log2(e)
   float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
   float gap;               // float(sample_gap) for the non-emulated merge
@@ -167,44 +178,62 @@ struct Item {
 // The per-row block counts are the only global-memory input of the decode; every role requests the NEXT item's
 // counts at the top of the current item (item_counts) and turns them into an Item one iteration later (make_item),
 // so no role stalls on a dependent load at an item boundary.
+// Claim order -> (head, tile pair).  Inside a head the pairs are formed from the LAST query tile backwards -- pair 0 =
+// tiles (nq-1, nq-2) -- so the rows the reference forces to full density (the last two query rows of every
+// CogVideoX head, C:241-246: 139 blocks instead of ~16) share ONE item instead of idling the partner stream of two.
+// Claims run: pair 0 of every head first (those items are up to 6x longer than the rest; started last they were the
+// tail: list scheduling 724 steps vs 613 with them first, mean 608), then the remaining pairs head-major (K/V of
+// ~2 heads stay L2-resident); the last num_solo_pairs claims are issued as two solo tiles each.
+__device__ __forceinline__ int pair_id_of(const AttnParams& p, int item) {
+  const int c = item < p.num_pair_items ? item : p.num_pair_items + ((item - p.num_pair_items) >> 1);
+  const int bh_n = p.B * p.H, pph = p.pairs_per_head;
+  if (pph == 1) return c;
+  if (c < bh_n) return c * pph;
+  const int j = c - bh_n;
+  return (j / (pph - 1)) * pph + 1 + j % (pph - 1);
+}
+__device__ __forceinline__ int tile_of(const AttnParams& p, int pair, int t) { return p.nq - 1 - (2 * pair + t); }
 __device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& c0, int& c1) {
   c0 = c1 = 0;
   if (item >= p.num_items) return;
   if (item < p.num_pair_items) {
-    const int bh = item / p.pairs_per_head, pair = item % p.pairs_per_head;
-    const int32_t* row = p.cnt + static_cast<int64_t>(bh) * p.nq + 2 * pair;
-    c0 = __ldg(row);
-    if (2 * pair + 1 < p.nq) c1 = __ldg(row + 1);
+    const int pid = pair_id_of(p, item);
+    const int bh = pid / p.pairs_per_head, pair = pid % p.pairs_per_head;
+    const int32_t* row = p.cnt + static_cast<int64_t>(bh) * p.nq;
+    c0 = __ldg(row + tile_of(p, pair, 0));
+    if (2 * pair + 1 < p.nq) c1 = __ldg(row + tile_of(p, pair, 1));
   } else {
     const int s = item - p.num_pair_items;
-    const int pid = p.num_pair_items + (s >> 1);
+    const int pid = pair_id_of(p, item);
     const int bh = pid / p.pairs_per_head;
-    const int qb = 2 * (pid % p.pairs_per_head) + (s & 1);
-    if (qb < p.nq) c0 = c1 = __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
+    const int qb = tile_of(p, pid % p.pairs_per_head, s & 1);
+    if (qb >= 0) c0 = c1 = __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
   }
 }
 __device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0, int c1) {
   Item it;
   const int npt = p.n_pool_tiles;
   if (item < p.num_pair_items) {
-    it.bh = item / p.pairs_per_head;
-    const int pair = item % p.pairs_per_head;
+    const int pid = pair_id_of(p, item);
+    it.bh = pid / p.pairs_per_head;
+    const int pair = pid % p.pairs_per_head;
     it.merge = false;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      const int qb = 2 * pair + t;
-      const bool valid = qb < p.nq;
-      it.qb[t] = qb;
+      const int qb = tile_of(p, pair, t);
+      const bool valid = qb >= 0;
+      it.qb[t] = valid ? qb : p.nq;  // p.nq = "no tile" for the roles' qb < nq checks
       it.pt[t] = valid ? npt : 0;
       it.off[t] = 0;
       it.ns[t] = valid ? (t ? c1 : c0) : 0;
     }
   } else {
     const int s = item - p.num_pair_items;
-    const int pid = p.num_pair_items + (s >> 1);
+    const int pid = pair_id_of(p, item);
     it.bh = pid / p.pairs_per_head;
-    const int qb = 2 * (pid % p.pairs_per_head) + (s & 1);
-    const bool valid = qb < p.nq;
+    const int qbr = tile_of(p, pid % p.pairs_per_head, s & 1);
+    const bool valid = qbr >= 0;
+    const int qb = valid ? qbr : p.nq;
     const int c = valid ? c0 : 0;
     // balance pooled + a  against  c - a tiles
     int a = c;
@@ -257,6 +286,10 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&mz->kv_full[s], 1);
       mbar_init(&mz->kv_empty[s], 1);
     }
+    for (int s = 0; s < kItemSlots; ++s) {
+      mbar_init(&mz->item_full[s], 1);
+      mbar_init(&mz->item_empty[s], 1 + 2 * kSoftmaxThreads / 32);  // issuer warp + every softmax warp
+    }
     fence_barrier_init();
   }
   if (warp == 11) tmem_alloc<512>(&mz->tmem_base);
@@ -283,11 +316,29 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     setmaxnreg_dec<kRegsOther>();
     uint32_t slot = 0, ph = 0;  // ring position / phase of the NEXT load
     uint32_t q_it[2] = {0, 0};
+    int n_claimed = 0;
+    auto claim = [&]() {
+      int v = 0;
+      if (lane == 0) v = p.sched ? atomicAdd(p.sched, 1) : static_cast<int>(blockIdx.x + n_claimed * gridDim.x);
+      ++n_claimed;
+      return __shfl_sync(0xffffffffu, v, 0);
+    };
     int c0n, c1n;
-    item_counts(p, blockIdx.x, c0n, c1n);
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    int next_item = claim();
+    item_counts(p, next_item, c0n, c1n);
+    for (int qk = 0;; ++qk) {
+      const int item = next_item;
+      const int qslot = qk & (kItemSlots - 1);
+      mbar_wait(&mz->item_empty[qslot], ((qk / kItemSlots) & 1) ^ 1);
+      if (lane == 0) {
+        mz->items[qslot] = make_int4(item < p.num_items ? item : -1, c0n, c1n, 0);
+        mbar_arrive(&mz->item_full[qslot]);
+      }
+      __syncwarp();
+      if (item >= p.num_items) break;
       const Item it = make_item(p, item, c0n, c1n);
-      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
+      next_item = claim();                          // one item ahead: the counts are in flight during this item
+      item_counts(p, next_item, c0n, c1n);
       const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
       int ns[2], nt[2];
@@ -365,11 +416,15 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t g[2] = {0, 0};
     uint32_t q_it[2] = {0, 0};
     const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
-    int c0n, c1n;
-    item_counts(p, blockIdx.x, c0n, c1n);
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = make_item(p, item, c0n, c1n);
-      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
+    for (int qk = 0;; ++qk) {
+      const int qslot = qk & (kItemSlots - 1);
+      mbar_wait(&mz->item_full[qslot], (qk / kItemSlots) & 1);
+      const int4 qe = mz->items[qslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mz->item_empty[qslot]);
+      if (qe.x < 0) break;
+      const int item = qe.x;
+      const Item it = make_item(p, item, qe.y, qe.z);
       const int nt[2] = {it.pt[0] + it.ns[0], it.pt[1] + it.ns[1]};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -460,11 +515,15 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int pool_tail = p.n_pool - (npt - 1) * kBlockN;
     const int seq_tail = p.Sk - (p.nk - 1) * kBlockN;  // valid keys in the last key block
 
-    int c0n, c1n;
-    item_counts(p, blockIdx.x, c0n, c1n);
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = make_item(p, item, c0n, c1n);
-      item_counts(p, item + gridDim.x, c0n, c1n);  // in flight until the next iteration
+    for (int qk = 0;; ++qk) {
+      const int qslot = qk & (kItemSlots - 1);
+      mbar_wait(&mz->item_full[qslot], (qk / kItemSlots) & 1);
+      const int4 qe = mz->items[qslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mz->item_empty[qslot]);
+      if (qe.x < 0) break;
+      const int item = qe.x;
+      const Item it = make_item(p, item, qe.y, qe.z);
       const int bh = it.bh;
       const int b = bh / p.H, h = bh % p.H;
       const int qb = t ? it.qb[1] : it.qb[0];  // selects, not indexing: keeps Item in registers
@@ -819,6 +878,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #ifdef BLADE_TRACE
 static long long* g_trace_buf = nullptr;
 #endif
+static thread_local int g_sched_prezeroed = 0;  // blade_asa_forward zeroes the item counter ahead of the mask kernels
+void attn_sched_prezeroed() { g_sched_prezeroed = 1; }
 static thread_local int g_sub64_next = 0;  // set by blade_block_sparse_attn64_fwd / blade_asa_attn64_fwd for one launch
 
 static int device_sm_count() {
@@ -831,7 +892,10 @@ static int device_sm_count() {
   return n;
 }
 
-size_t attn_park_bytes(int64_t D) { return static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16; }
+// attention workspace: [0, 256) the item counter, then per CTA and stream one parked pooled-branch tile
+size_t attn_park_bytes(int64_t D) {
+  return kSchedBytes + static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16;
+}
 
 static float round_host(float x, bool bf16) {
   return bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
@@ -896,7 +960,9 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.out_ss = out->stride[2];
   p.lse = lse;
   p.dst_row = dst_row;
-  p.park = static_cast<uint4*>(workspace);
+  static const bool static_sched = getenv("BLADE_STATIC_SCHED") && atoi(getenv("BLADE_STATIC_SCHED")) != 0;  // A/B knob
+  p.sched = workspace && ws_bytes >= kSchedBytes && !static_sched ? static_cast<int*>(workspace) : nullptr;
+  p.park = workspace ? reinterpret_cast<uint4*>(static_cast<uint8_t*>(workspace) + kSchedBytes) : nullptr;
   p.B = (int)B;
   p.H = (int)H;
   p.S = (int)S;
@@ -907,13 +973,21 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.n_pool_tiles = pooled ? (int)ceil_div(n_pool, kBlockN) : 0;
   p.pairs_per_head = (nq + 1) / 2;
   {
-    // tail round: if the leftover pairs would fill at most half of the CTAs, run them as solo tiles with the KV
-    // list split across the two streams (BLADE_NO_SPLIT=1 disables, for A/B timing)
+    // tail: the last pairs are issued as solo tiles with the KV list split across the two streams, so the last
+    // claims are half-length items (BLADE_NO_SPLIT=1 disables, for A/B timing).  With the dynamic queue that is
+    // the last G/2 pairs (one solo per CTA); with the static sequence only a leftover round that fills at most half
+    // of the CTAs.
     static const bool no_split = getenv("BLADE_NO_SPLIT") && atoi(getenv("BLADE_NO_SPLIT")) != 0;
     const int np = (int)(B * H) * p.pairs_per_head, G = device_sm_count();
-    const int r = np % G;
-    const int split = (!no_split && r > 0 && 2 * r <= G) ? r : 0;
+    int split = 0;
+    if (!no_split) {
+      const int r = np % G;
+      if (np < G) split = 2 * np <= G ? np : 0;
+      else if (p.sched) split = G / 2;
+      else split = (r > 0 && 2 * r <= G) ? r : 0;
+    }
     p.num_pair_items = np - split;
+    p.num_solo_pairs = split;
     p.num_items = p.num_pair_items + 2 * split;
   }
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
@@ -933,6 +1007,8 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
 #endif
 
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
+  if (p.sched && !g_sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, sizeof(int), stream));
+  g_sched_prezeroed = 0;
   StageTimer timer(3, stream);
 #define LAUNCH_ATTN(DD, BF)                                                                                     \
   do {                                                                                                          \

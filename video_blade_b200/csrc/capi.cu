@@ -22,6 +22,7 @@ StageEvents* stage_events() {
 }
 
 size_t attn_park_bytes(int64_t D);
+void attn_sched_prezeroed();
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
                 int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
@@ -188,6 +189,8 @@ extern "C" int blade_gilbert_tables(int32_t width, int32_t height, int32_t depth
   return BLADE_OK;
 }
 
+extern "C" size_t blade_attn_workspace_bytes(int64_t D) { return attn_park_bytes(D); }
+
 extern "C" size_t blade_asa_workspace_bytes(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg) {
   if (!cfg) return 0;
   return carve(B, H, S, D, cfg).total;
@@ -220,6 +223,9 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   int32_t* idx = idx_out ? idx_out : reinterpret_cast<int32_t*>(ws + w.idx);
   int32_t* cnt = cnt_out ? cnt_out : reinterpret_cast<int32_t*>(ws + w.cnt);
 
+  // the attention kernel's item counter (head of its workspace) is zeroed here, ahead of the mask kernels, so the
+  // memset is not on the path between the selection and the attention launch
+  BLADE_CUDA_OK(cudaMemsetAsync(ws + w.park, 0, sizeof(int), stream));
   const bool need_means = scores_in == nullptr;
   // gather / rotate / block means on the caller's stream ...
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
@@ -279,9 +285,11 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
       kp.stride[i] = vp.stride[i] = ps[i];
     }
     kp.dtype = vp.dtype = q->dtype;
+    attn_sched_prezeroed();
     return launch_attn(&qr, &kr, &vr, idx, cnt, nb, &kp, &vp, cfg->sample_gap, out, nullptr, dst_row, scale,
                        cfg->exact_merge, ws + w.park, attn_park_bytes(D), stream);
   }
+  attn_sched_prezeroed();
   return launch_attn(&qr, &kr, &vr, idx, cnt, nb, nullptr, nullptr, 0, out, nullptr, dst_row, scale, 0, ws + w.park,
                      attn_park_bytes(D), stream);
 }
