@@ -518,3 +518,27 @@ def test_split_tail_matches_unsplit_schedule():
         outs.append(torch.load(path))
         os.remove(path)
     _close(outs[0], outs[1], 4e-3, 1.6e-2)
+
+
+def test_many_items_per_cta_nonuniform_rows_vs_torch_fp32():
+    """5 120 tile pairs on 148 CTAs (the item queue wraps ~8 times), B = 2, rows keeping 2..40 of 64 blocks, ragged
+    last block: every 10th head against a plain fp32 torch attention with the token-level mask."""
+    eng = _engine(use_rearrange=False)
+    B, H, S, D, nb = 2, 80, 64 * 128 - 37, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q, k, v = (torch.randn(B, S, H, D, device="cuda", generator=g).to(torch.bfloat16).transpose(1, 2) for _ in range(3))
+    score = torch.rand(B, H, nb, nb, device="cuda", generator=g)
+    counts = torch.randint(2, 41, (B, H, nb, 1), device="cuda", generator=g)
+    kth = torch.sort(score, dim=-1, descending=True).values.gather(-1, counts - 1)
+    mask = score >= kth
+    idx, cnt = eng.mask_to_index(mask)
+    assert torch.equal(cnt.long(), counts[..., 0])
+    out, lse = eng.block_sparse_attn(q, k, v, idx, cnt)
+    for b in range(B):
+        for h in range(0, H, 10):
+            tok = mask[b, h].repeat_interleave(128, 0).repeat_interleave(128, 1)[:S, :S]
+            s = (q[b, h].float() @ k[b, h].float().T) / D ** 0.5
+            s = s.masked_fill(~tok, float("-inf"))
+            want = torch.softmax(s, -1) @ v[b, h].float()
+            _close(out[b, h], want.to(torch.bfloat16))
+            _close(lse[b, h], torch.logsumexp(s, -1), 1e-5, 1e-4)
