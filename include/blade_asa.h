@@ -63,6 +63,18 @@ typedef struct BladeTensor {
   int32_t _pad;
 } BladeTensor;
 
+/* q/k normalisation of the attention processor, fused into the gather (MW:99-102: `attn.norm_q(query)`,
+ * `attn.norm_k(key)` between the projections and the head split; Wan2.1 uses RMSNorm over all heads' channels).
+ * kind 1: y = x * rsqrt(mean_c(x^2) + eps) * w in fp32, rounded once to the tensor dtype;
+ * kind 2: diffusers' RMSNorm rounding: (x * rstd) -> tensor dtype, then * w -> tensor dtype.
+ * q and k must be token-major ([B,S,H*D] memory: stride_h == D, stride_s == H*D); weights [H*D] in the tensor dtype. */
+typedef struct BladeQkNorm {
+  int32_t kind;          /* 0 = none */
+  float eps;
+  const void* q_weight;  /* device */
+  const void* k_weight;  /* device */
+} BladeQkNorm;
+
 /* Knobs of the reference module (W:9-16, C:9-16 and the literals W:62,325,341). */
 typedef struct BladeAsaConfig {
   int32_t block_size;        /* 128 (W:325); 64 accepted for the selection/score stages */
@@ -77,7 +89,8 @@ typedef struct BladeAsaConfig {
   int32_t rope_first_row;    /* first source row that is rotated (0 wan; text_length cog, MC:59-64) */
   const float* rope_cos_sin; /* device, fp32 [rows, D/2, 2] (cos, sin) per token and pair, or NULL: rotary embedding
                                 fused into the gather, applied to q and k where the processor does (MW:108-116) */
-  int32_t reserved[4];
+  const BladeQkNorm* qk_norm; /* host pointer or NULL (blade_asa_forward only; needs the output copies, i.e. a gather) */
+  int32_t reserved[2];
 } BladeAsaConfig;
 
 /* ---- introspection -------------------------------------------------------------------------- */

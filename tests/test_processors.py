@@ -115,3 +115,37 @@ def test_cog_processor_end_to_end():
             assert float(dd.norm() / b_.float().norm()) <= 1e-2
     finally:
         C.width, C.height, C.depth, C.text_length, C.max_retain_ratio = 45, 30, 13, 226, 0.1
+
+
+@pytest.mark.gpu
+def test_wan_processor_fused_qk_norm_matches_torch_norm():
+    """RMSNorm over all heads' channels (MW:99-102) inside the gather kernel == the module's own forward followed by
+    the unfused path, up to bf16 rounding of the normalised q/k."""
+    import torch
+    from video_blade_b200 import wanx_blocksparseattn as W
+    from video_blade_b200.modify_wan import Attention, WanAttnProcessor2_0
+    from video_blade_b200.dit import rope_freqs
+    torch.manual_seed(0)
+    old = (W.width, W.height, W.depth)
+    W.width, W.height, W.depth = 26, 15, 8
+    try:
+        S, dim, heads = 26 * 15 * 8, 512, 4
+        attn = Attention(dim, heads, qk_norm="rms_norm_across_heads").cuda().to(torch.bfloat16)
+        with torch.no_grad():
+            attn.norm_q.weight.copy_(1 + 0.3 * torch.randn(dim))
+            attn.norm_k.weight.copy_(1 + 0.3 * torch.randn(dim))
+        inner = W.AdaptiveBlockSparseAttnTrain()
+        inner.print_every = 0
+        attn.inner_attention = inner
+        x = torch.randn(2, S, dim, device="cuda", dtype=torch.bfloat16)
+        rope = rope_freqs(8, 15, 26, dim // heads, device="cuda")
+        outs = []
+        for fuse in (False, True):
+            attn.set_processor(WanAttnProcessor2_0(fuse_norm=fuse))
+            with torch.no_grad():
+                outs.append(attn(x, rotary_emb=rope).float())
+        d = outs[1] - outs[0]
+        rel = float(d.norm() / outs[0].norm())
+        assert rel < 1e-2, rel
+    finally:
+        W.width, W.height, W.depth = old

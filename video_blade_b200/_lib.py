@@ -20,11 +20,16 @@ class BladeTensor(C.Structure):
                 ("dtype", C.c_int32), ("_pad", C.c_int32)]
 
 
+class BladeQkNorm(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p)]
+
+
 class BladeAsaConfig(C.Structure):
     _fields_ = [("block_size", C.c_int32), ("sample_gap", C.c_int32), ("min_retain", C.c_int32),
                 ("max_retain", C.c_int32), ("energy_threshold", C.c_float), ("force_last", C.c_int32),
                 ("num_keep", C.c_int32), ("estimator", C.c_int32), ("exact_merge", C.c_int32),
-                ("rope_first_row", C.c_int32), ("rope_cos_sin", C.c_void_p), ("reserved", C.c_int32 * 4)]
+                ("rope_first_row", C.c_int32), ("rope_cos_sin", C.c_void_p), ("qk_norm", C.POINTER(BladeQkNorm)),
+                ("reserved", C.c_int32 * 2)]
 
 
 # every symbol include/blade_asa.h declares (tests/test_cabi_symbols.py checks the list against the header)

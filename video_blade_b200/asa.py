@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BladeAsaConfig, check, current_stream, ptr, tensor_desc
+from ._lib import BladeQkNorm, BladeAsaConfig, check, current_stream, ptr, tensor_desc
 
 
 @dataclass
@@ -313,10 +313,12 @@ class AsaEngine:
 
     # ---- the whole layer ------------------------------------------------------------------
     def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
-                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None):
+                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None, qk_norm=None):
         """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
         token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
-        processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous."""
+        processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous.
+        `qk_norm` (optional): (kind, q_weight [H*D], k_weight [H*D], eps) -- the processor's RMSNorm over all heads'
+        channels (MW:99-102), applied to q and k inside the gather kernel (include/blade_asa.h: BladeQkNorm)."""
         self._require_cuda(q, k, v, scores)
         B, H, S, D = q.shape
         kn = self.knobs
@@ -325,9 +327,20 @@ class AsaEngine:
             if virtual_rows is not None:
                 raise ValueError("staged path (sampled_max / block 64): the packed Ulysses receive layout is not wired yet")
             qo, ko = sample_offsets if sample_offsets is not None else (None, None)
+            if qk_norm is not None:
+                raise ValueError("staged path (sampled_max / block 64): fused q/k norm is not wired")
             return self._forward_staged(q, k, v, qo, ko, return_debug, scores=scores, rope=rope)
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
+        norm_keep = None
+        if qk_norm is not None:
+            if virtual_rows is not None:
+                raise ValueError("fused q/k norm: not available on the packed Ulysses receive layout")
+            kind, wq, wk, eps = qk_norm
+            assert wq.dtype == q.dtype and wk.dtype == q.dtype and wq.numel() == H * D and wk.numel() == H * D
+            wq, wk = wq.contiguous(), wk.contiguous()
+            norm_keep = BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr())
+            cfg.qk_norm = C.pointer(norm_keep)
         if rope is not None:
             if virtual_rows is not None:
                 raise ValueError("fused rotary embedding: not available on the packed Ulysses receive layout")

@@ -122,7 +122,7 @@ static ForkState* fork_state() {
 
 // workspace carving for blade_asa_forward
 struct ForwardWs {
-  size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, total;
+  size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, rstd, total;
 };
 static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg) {
   ForwardWs w{};
@@ -146,6 +146,7 @@ static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAs
   w.idx = take(B * H * nb * nb * 4);
   w.cnt = take(B * H * nb * 4);
   w.park = take(attn_park_bytes(D));
+  w.rstd = take(2 * B * S * 4);  // q/k RMSNorm statistic (BladeQkNorm)
   w.total = off;
   return w;
 }
@@ -216,7 +217,16 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const int64_t nb = ceil_div(S, cfg->block_size);
   const int64_t np = cfg->sample_gap > 0 ? ceil_div(S, cfg->sample_gap) : 0;
-  const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr;  // rotation needs the output copies too
+  const bool norm_on = cfg->qk_norm != nullptr && cfg->qk_norm->kind != 0;
+  const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr || norm_on;  // these need the output copies
+  PrepNorm pn{};
+  if (norm_on) {
+    pn.kind = cfg->qk_norm->kind;
+    pn.eps = cfg->qk_norm->eps;
+    pn.q_weight = cfg->qk_norm->q_weight;
+    pn.k_weight = cfg->qk_norm->k_weight;
+    pn.rstd = reinterpret_cast<float*>(ws + w.rstd);
+  }
   float* q_mean = reinterpret_cast<float*>(ws + w.q_mean);
   float* k_mean = reinterpret_cast<float*>(ws + w.k_mean);
   float* scores = scores_out ? scores_out : reinterpret_cast<float*>(ws + w.scores);
@@ -231,7 +241,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
                         rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
-                        stream))
+                        stream, norm_on ? &pn : nullptr))
     return e;
   // ... then the bandwidth-bound gap pooling and the latency-bound score + selection kernels run concurrently on
   // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):

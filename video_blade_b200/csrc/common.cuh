@@ -48,9 +48,18 @@ struct StageTimer {
   }
 };
 
+// fused q/k RMSNorm (BladeQkNorm): rstd = device fp32 scratch [2][B*S] that prep_impl fills itself
+struct PrepNorm {
+  int kind;
+  float eps;
+  const void* q_weight;
+  const void* k_weight;
+  float* rstd;
+};
 int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
-              int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream);
+              int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream,
+              const PrepNorm* norm = nullptr);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

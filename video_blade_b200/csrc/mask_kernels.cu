@@ -65,6 +65,35 @@ struct Strides3 {
 };
 
 // ------------------------------------------------------------------------------------------------
+// q/k RMSNorm statistic (Wan: rms_norm_across_heads, MW:99-102): rstd[token] = rsqrt(mean over all H*D channels of
+// x^2 + eps) for q and k.  One warp per token row ([B,S,H*D] memory, a contiguous 2*H*D-byte segment), 16-byte loads.
+// out: fp32 [2][B*S] (q then k).  The normalisation itself happens inside prep_block_kernel.
+// ------------------------------------------------------------------------------------------------
+template <bool IS_BF16>
+__global__ void __launch_bounds__(256) rms_stat_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                       int64_t q_sb, int64_t q_ss, int64_t k_sb, int64_t k_ss, int S,
+                                                       int64_t rows, int hd, float eps, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const int64_t b = row / S, sidx = row % S;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const uint16_t* src = t == 0 ? q + b * q_sb + sidx * q_ss : k + b * k_sb + sidx * k_ss;
+    float acc = 0.f;
+    for (int c = lane; c < hd / 8; c += 32) {
+      float f[8];
+      unpack8<IS_BF16>(ldg_stream(reinterpret_cast<const uint4*>(src) + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(f[i], f[i], acc);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[t * rows + row] = rsqrtf(acc / static_cast<float>(hd) + eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // prep: grid (nb, H, B), 256 threads.  One CTA = one block of `block` output rows of one head.
 // ------------------------------------------------------------------------------------------------
 template <int D, bool IS_BF16, bool COPY, bool ROPE>
@@ -74,7 +103,9 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
                                                          uint16_t* __restrict__ q_r, uint16_t* __restrict__ k_r,
                                                          uint16_t* __restrict__ v_r, float* __restrict__ q_mean,
                                                          float* __restrict__ k_mean, int S, int H, int nb, int block,
-                                                         const float* __restrict__ rope, int rope_first) {
+                                                         const float* __restrict__ rope, int rope_first,
+                                                         const float* __restrict__ rstd, const uint16_t* __restrict__ wq,
+                                                         const uint16_t* __restrict__ wk, int norm_kind) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -115,6 +146,30 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
         const int sr = src_row ? __ldg(src_row + rc) : rc;
         srcs[u] = sr;
         if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
+      }
+      if (rstd != nullptr && t < 2) {
+        // q/k RMSNorm of the processor (MW:99-102), statistic from rms_stat_kernel; weights of this head's columns
+        float w[8];
+        unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>((t == 0 ? wq : wk) + h * D) + chunk), w);
+        const float* rs = rstd + static_cast<int64_t>(t) * gridDim.z * S + static_cast<int64_t>(b) * S;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (p0 + u >= passes) continue;
+          const float r = __ldg(rs + srcs[u]);
+          float f[8];
+          unpack8<IS_BF16>(val[u], f);
+          if (norm_kind == 2) {  // diffusers: (x * rstd) -> tensor dtype, then * weight
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= r;
+            unpack8<IS_BF16>(pack8<IS_BF16>(f), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= w[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = f[i] * r * w[i];
+          }
+          val[u] = pack8<IS_BF16>(f);
+        }
       }
       if (ROPE && t < 2) {
         // rotary embedding where the reference applies it (modify_wan.py:108-116 / modify_cogvideo.py:59-64):
@@ -622,7 +677,7 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
 int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
                      void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool,
                      int32_t block_size, int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row,
-                     int parts, cudaStream_t stream) {
+                     int parts, cudaStream_t stream, const PrepNorm* norm) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -646,6 +701,35 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   StageTimer timer(parts == 2 ? -1 : 0, stream);
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
+  const float* rstd = nullptr;
+  const uint16_t *wq = nullptr, *wk = nullptr;
+  int norm_kind = 0;
+  if (norm && norm->kind != 0 && (parts & 1)) {
+    BLADE_REQUIRE(norm->kind == 1 || norm->kind == 2, BLADE_ERR_ARG, "qk_norm kind %d not in {1,2}", norm->kind);
+    BLADE_REQUIRE(copy, BLADE_ERR_ARG, "qk_norm needs the q_r/k_r/v_r outputs");
+    BLADE_REQUIRE(norm->q_weight && norm->k_weight && norm->rstd, BLADE_ERR_ARG, "qk_norm weights / scratch missing");
+    for (const BladeTensor* t : {q, k})
+      BLADE_REQUIRE(t->stride[1] == D && t->stride[2] == H * D, BLADE_ERR_SHAPE,
+                    "qk_norm needs token-major q/k ([B,S,H*D] memory)");
+    BLADE_REQUIRE((reinterpret_cast<uintptr_t>(norm->q_weight) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(norm->k_weight) & 15) == 0,
+                  BLADE_ERR_ALIGN, "qk_norm weights not 16B aligned");
+    const int64_t rows = B * S;
+    const unsigned sgrid = static_cast<unsigned>(ceil_div(rows, 8));
+    if (bf)
+      rms_stat_kernel<true><<<sgrid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
+                                                       static_cast<int>(S), rows, static_cast<int>(H * D), norm->eps,
+                                                       norm->rstd);
+    else
+      rms_stat_kernel<false><<<sgrid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
+                                                        static_cast<int>(S), rows, static_cast<int>(H * D), norm->eps,
+                                                        norm->rstd);
+    BLADE_CUDA_OK(cudaGetLastError());
+    rstd = norm->rstd;
+    wq = static_cast<const uint16_t*>(norm->q_weight);
+    wk = static_cast<const uint16_t*>(norm->k_weight);
+    norm_kind = norm->kind;
+  }
   if ((parts & 1) && (q_mean || k_mean || copy)) {
     dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
 #define LAUNCH_PREP(DD, BF, CP, RP)                                                                               \
@@ -653,7 +737,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
                                                               static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
                                                               static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
                                                               static_cast<int>(S), static_cast<int>(H), nb, block_size, \
-                                                              rope_cos_sin, rope_first_row)
+                                                              rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind)
 #define LAUNCH_PREP_D(DD)                                                                                             \
   do {                                                                                                                \
     if (rope_cos_sin) {                                                                                               \

@@ -44,8 +44,9 @@ def _rope_table(freqs: torch.Tensor) -> torch.Tensor:
 class WanAttnProcessor2_0:
     """MW:75-148."""
 
-    def __init__(self, fuse_rope: bool = True):
+    def __init__(self, fuse_rope: bool = True, fuse_norm: bool = True):
         self.fuse_rope = fuse_rope
+        self.fuse_norm = fuse_norm      # q/k RMSNorm inside the gather kernel instead of ~14 element-wise launches
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -59,10 +60,16 @@ class WanAttnProcessor2_0:
         query = attn.to_q(hidden_states)                                       # MW:95-97
         key = attn.to_k(encoder_hidden_states)
         value = attn.to_v(encoder_hidden_states)
-        if attn.norm_q is not None:                                            # MW:99-102
-            query = attn.norm_q(query)
-        if attn.norm_k is not None:
-            key = attn.norm_k(key)
+        fused_norm = None
+        if self.fuse_norm and _norm_fusable(attn, query, encoder_hidden_states is hidden_states):
+            nq, nk = attn.norm_q, attn.norm_k
+            fused_norm = (2 if getattr(nq, "_two_roundings", False) else 1, nq.weight.detach(), nk.weight.detach(),
+                          float(nq.eps))
+        else:
+            if attn.norm_q is not None:                                        # MW:99-102
+                query = attn.norm_q(query)
+            if attn.norm_k is not None:
+                key = attn.norm_k(key)
         query = query.unflatten(2, (attn.heads, -1)).transpose(1, 2)           # MW:104-106: strided views
         key = key.unflatten(2, (attn.heads, -1)).transpose(1, 2)
         value = value.unflatten(2, (attn.heads, -1)).transpose(1, 2)
@@ -84,8 +91,13 @@ class WanAttnProcessor2_0:
             hidden_states_img = attn.inner_attention(query, key_img, value_img)
             hidden_states_img = hidden_states_img.transpose(1, 2).flatten(2, 3).type_as(query)
 
-        if fused_rope is not None:
-            hidden_states = attn.inner_attention(query, key, value, rotary=fused_rope)
+        if fused_rope is not None or fused_norm is not None:
+            kw = {}
+            if fused_rope is not None:
+                kw["rotary"] = fused_rope
+            if fused_norm is not None:
+                kw["qk_norm"] = fused_norm
+            hidden_states = attn.inner_attention(query, key, value, **kw)
         else:
             hidden_states = attn.inner_attention(query, key, value)            # MW:135
         hidden_states = hidden_states.transpose(1, 2).flatten(2, 3)            # a view: output memory is [B,S,H,D]
@@ -95,6 +107,22 @@ class WanAttnProcessor2_0:
         hidden_states = attn.to_out[0](hidden_states)                          # MW:146-147
         hidden_states = attn.to_out[1](hidden_states)
         return hidden_states
+
+
+def _norm_fusable(attn, query, self_attention: bool) -> bool:
+    """The fused path covers the Wan2.1 configuration: RMSNorm over all heads' channels on q and k, weights in the
+    activation dtype, self-attention, no image branch."""
+    nq, nk = getattr(attn, "norm_q", None), getattr(attn, "norm_k", None)
+    if nq is None or nk is None or not self_attention or getattr(attn, "add_k_proj", None) is not None:
+        return False
+    if not getattr(attn.inner_attention, "supports_fused_qk_norm", False) or not query.is_cuda:
+        return False
+    for n in (nq, nk):
+        w = getattr(n, "weight", None)
+        if type(n).__name__ != "RMSNorm" or w is None or w.dtype != query.dtype or w.numel() != query.shape[-1] \
+                or getattr(n, "bias", None) is not None:
+            return False
+    return True
 
 
 def set_adaptive_block_sparse_attn_wanx(model, verbose=False):
