@@ -73,6 +73,9 @@ typedef struct BladeQkNorm {
   float eps;
   const void* q_weight;  /* device */
   const void* k_weight;  /* device */
+  const float* rstd;     /* optional device fp32 [2][B*S] (q then k), indexed by TOKEN: a statistic computed elsewhere
+                            (blade_qk_rms_stat on the token shard + all-gather, when the heads are sharded); NULL =
+                            computed here, which needs token-major q/k */
 } BladeQkNorm;
 
 /* Knobs of the reference module (W:9-16, C:9-16 and the literals W:62,325,341). */
@@ -90,7 +93,9 @@ typedef struct BladeAsaConfig {
   const float* rope_cos_sin; /* device, fp32 [rows, D/2, 2] (cos, sin) per token and pair, or NULL: rotary embedding
                                 fused into the gather, applied to q and k where the processor does (MW:108-116) */
   const BladeQkNorm* qk_norm; /* host pointer or NULL (blade_asa_forward only; needs the output copies, i.e. a gather) */
-  int32_t reserved[2];
+  const int32_t* token_row;   /* optional device int32 [S]: token index of output row r, for the rotary table and the
+                                 norm statistic, when src_row addresses a packed buffer instead of tokens (Ulysses
+                                 receive layout); NULL = src_row[r] (or r) is the token index */
 } BladeAsaConfig;
 
 /* ---- introspection -------------------------------------------------------------------------- */
@@ -130,6 +135,10 @@ int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, const BladeT
                         float* q_mean, float* k_mean, void* k_pool, void* v_pool,
                         int32_t block_size, int32_t sample_gap,
                         const float* rope_cos_sin, int32_t rope_first_row, void* stream);
+
+/* rstd[token] = rsqrt(mean over all H*D channels of x^2 + eps) for q and k (token-major [B,S,H*D] memory):
+ * rstd_out fp32 [2][B*S].  The statistic half of BladeQkNorm, for callers that shard heads after computing it. */
+int blade_qk_rms_stat(const BladeTensor* q, const BladeTensor* k, float eps, float* rstd_out, void* stream);
 
 /* ---- score estimators: fp32 [B,H,nb,nb] row-normalised block scores -------------------------- */
 int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores,

@@ -21,7 +21,8 @@ class BladeTensor(C.Structure):
 
 
 class BladeQkNorm(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p)]
+    _fields_ = [("kind", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p),
+                ("rstd", C.c_void_p)]
 
 
 class BladeAsaConfig(C.Structure):
@@ -29,7 +30,7 @@ class BladeAsaConfig(C.Structure):
                 ("max_retain", C.c_int32), ("energy_threshold", C.c_float), ("force_last", C.c_int32),
                 ("num_keep", C.c_int32), ("estimator", C.c_int32), ("exact_merge", C.c_int32),
                 ("rope_first_row", C.c_int32), ("rope_cos_sin", C.c_void_p), ("qk_norm", C.POINTER(BladeQkNorm)),
-                ("reserved", C.c_int32 * 2)]
+                ("token_row", C.c_void_p)]
 
 
 # every symbol include/blade_asa.h declares (tests/test_cabi_symbols.py checks the list against the header)
@@ -39,7 +40,7 @@ SYMBOLS = [
     "blade_mask_to_index", "blade_block_sparse_attn_fwd", "blade_asa_attn_fwd", "blade_asa_forward",
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
     "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
-    "blade_attn_workspace_bytes",
+    "blade_attn_workspace_bytes", "blade_qk_rms_stat",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -63,6 +64,7 @@ def load() -> C.CDLL:
     lib.blade_gilbert_tables.argtypes = [i32, i32, i32, vp, vp]
     lib.blade_asa_workspace_bytes.argtypes = [i64, i64, i64, i64, CFG]
     lib.blade_asa_workspace_bytes.restype = C.c_size_t
+    lib.blade_qk_rms_stat.argtypes = [T, T, f32, vp, vp]
     lib.blade_attn_workspace_bytes.argtypes = [i64]
     lib.blade_attn_workspace_bytes.restype = C.c_size_t
     lib.blade_asa_prep.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]

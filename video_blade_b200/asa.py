@@ -311,6 +311,16 @@ class AsaEngine:
             current_stream()))
         return out
 
+    def qk_rms_stat(self, q, k, eps: float):
+        """rstd of the processor's RMSNorm over all heads' channels (MW:99-102) for q and k: fp32 [2, B*S].
+        q, k: [B,H,S,D] views of token-major [B,S,H*D] memory."""
+        self._require_cuda(q, k)
+        B, H, S, D = q.shape
+        out = torch.empty(2, B * S, dtype=torch.float32, device=q.device)
+        check(self.lib.blade_qk_rms_stat(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), float(eps), out.data_ptr(),
+                                         current_stream()))
+        return out
+
     # ---- the whole layer ------------------------------------------------------------------
     def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
                 virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None, qk_norm=None):
@@ -334,16 +344,17 @@ class AsaEngine:
         cfg = kn.c_config(nb)
         norm_keep = None
         if qk_norm is not None:
-            if virtual_rows is not None:
-                raise ValueError("fused q/k norm: not available on the packed Ulysses receive layout")
-            kind, wq, wk, eps = qk_norm
+            kind, wq, wk, eps = qk_norm[:4]
+            rstd = qk_norm[4] if len(qk_norm) > 4 else None      # statistic computed elsewhere, fp32 [2, B*S] by token
+            if virtual_rows is not None and rstd is None:
+                raise ValueError("fused q/k norm on the packed Ulysses layout needs the statistic (qk_rms_stat)")
             assert wq.dtype == q.dtype and wk.dtype == q.dtype and wq.numel() == H * D and wk.numel() == H * D
             wq, wk = wq.contiguous(), wk.contiguous()
-            norm_keep = BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr())
+            if rstd is not None:
+                assert rstd.dtype == torch.float32 and rstd.is_contiguous() and rstd.numel() == 2 * B * S
+            norm_keep = BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr(), ptr(rstd))
             cfg.qk_norm = C.pointer(norm_keep)
         if rope is not None:
-            if virtual_rows is not None:
-                raise ValueError("fused rotary embedding: not available on the packed Ulysses receive layout")
             table, first = rope
             assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[-2:] == (D // 2, 2)
             cfg.rope_cos_sin = table.data_ptr()
@@ -357,6 +368,15 @@ class AsaEngine:
             if key not in self._src_row:
                 self._src_row[key] = (virtual_rows[src.long()] if src is not None else virtual_rows).contiguous()
             src = self._src_row[key]
+            if rope is not None or qk_norm is not None:
+                # the rotary table and the norm statistic are indexed by token, not by packed-buffer row
+                tok = dst
+                if tok is None:
+                    tkey = ("arange", str(dev), S)
+                    if tkey not in self._src_row:
+                        self._src_row[tkey] = torch.arange(S, dtype=torch.int32, device=dev)
+                    tok = self._src_row[tkey]
+                cfg.token_row = tok.data_ptr()
         nbytes = self.lib.blade_asa_workspace_bytes(B, H, S, D, C.byref(cfg))
         ws = self.workspace(dev, nbytes)
         out = torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)

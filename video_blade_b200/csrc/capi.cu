@@ -226,6 +226,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     pn.q_weight = cfg->qk_norm->q_weight;
     pn.k_weight = cfg->qk_norm->k_weight;
     pn.rstd = reinterpret_cast<float*>(ws + w.rstd);
+    pn.rstd_ext = cfg->qk_norm->rstd;
   }
   float* q_mean = reinterpret_cast<float*>(ws + w.q_mean);
   float* k_mean = reinterpret_cast<float*>(ws + w.k_mean);
@@ -241,7 +242,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
                         rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
-                        stream, norm_on ? &pn : nullptr))
+                        stream, norm_on ? &pn : nullptr, cfg->token_row))
     return e;
   // ... then the bandwidth-bound gap pooling and the latency-bound score + selection kernels run concurrently on
   // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):

@@ -54,12 +54,14 @@ struct PrepNorm {
   float eps;
   const void* q_weight;
   const void* k_weight;
-  float* rstd;
+  float* rstd;            // scratch the statistic kernel fills ...
+  const float* rstd_ext;  // ... unless the caller brings the statistic (indexed by token)
 };
 int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
               int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream,
-              const PrepNorm* norm = nullptr);
+              const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr);
+int rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

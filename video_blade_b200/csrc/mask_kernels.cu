@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
                                                          float* __restrict__ k_mean, int S, int H, int nb, int block,
                                                          const float* __restrict__ rope, int rope_first,
                                                          const float* __restrict__ rstd, const uint16_t* __restrict__ wq,
-                                                         const uint16_t* __restrict__ wk, int norm_kind) {
+                                                         const uint16_t* __restrict__ wk, int norm_kind,
+                                                         const int32_t* __restrict__ tok_row) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
         rows[u] = r;
         const int rc = r < S ? r : S - 1;  // replicate padding (W:35)
         const int sr = src_row ? __ldg(src_row + rc) : rc;
-        srcs[u] = sr;
+        srcs[u] = tok_row ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
         if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
       }
       if (rstd != nullptr && t < 2) {
@@ -673,11 +674,40 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
                           rope_cos_sin, rope_first_row, 3, static_cast<cudaStream_t>(stream_));
 }
 
+int blade::rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream) {
+  if (int e = check_tensor16(q, "q")) return e;
+  if (int e = check_tensor16(k, "k")) return e;
+  BLADE_REQUIRE(out, BLADE_ERR_ARG, "rstd output null");
+  const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
+  for (const BladeTensor* t : {q, k}) {
+    BLADE_REQUIRE(t->shape[0] == B && t->shape[1] == H && t->shape[2] == S && t->shape[3] == D && t->dtype == q->dtype,
+                  BLADE_ERR_SHAPE, "q/k differ");
+    BLADE_REQUIRE(t->stride[1] == D && t->stride[2] == H * D, BLADE_ERR_SHAPE,
+                  "the RMSNorm statistic needs token-major q/k ([B,S,H*D] memory)");
+  }
+  BLADE_REQUIRE((H * D) % 8 == 0, BLADE_ERR_SHAPE, "H*D must be a multiple of 8");
+  const int64_t rows = B * S;
+  const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
+  const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr);
+  if (q->dtype == BLADE_BF16)
+    rms_stat_kernel<true><<<grid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
+                                                    static_cast<int>(S), rows, static_cast<int>(H * D), eps, out);
+  else
+    rms_stat_kernel<false><<<grid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
+                                                     static_cast<int>(S), rows, static_cast<int>(H * D), eps, out);
+  BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+extern "C" int blade_qk_rms_stat(const BladeTensor* q, const BladeTensor* k, float eps, float* rstd_out, void* stream) {
+  return blade::rms_stat_impl(q, k, eps, rstd_out, static_cast<cudaStream_t>(stream));
+}
+
 // parts: bit 0 = gather/copy/means kernel, bit 1 = gap-pooling kernel (reads the copies when they exist)
 int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
                      void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool,
                      int32_t block_size, int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row,
-                     int parts, cudaStream_t stream, const PrepNorm* norm) {
+                     int parts, cudaStream_t stream, const PrepNorm* norm, const int32_t* tok_row) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -707,25 +737,14 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   if (norm && norm->kind != 0 && (parts & 1)) {
     BLADE_REQUIRE(norm->kind == 1 || norm->kind == 2, BLADE_ERR_ARG, "qk_norm kind %d not in {1,2}", norm->kind);
     BLADE_REQUIRE(copy, BLADE_ERR_ARG, "qk_norm needs the q_r/k_r/v_r outputs");
-    BLADE_REQUIRE(norm->q_weight && norm->k_weight && norm->rstd, BLADE_ERR_ARG, "qk_norm weights / scratch missing");
-    for (const BladeTensor* t : {q, k})
-      BLADE_REQUIRE(t->stride[1] == D && t->stride[2] == H * D, BLADE_ERR_SHAPE,
-                    "qk_norm needs token-major q/k ([B,S,H*D] memory)");
+    BLADE_REQUIRE(norm->q_weight && norm->k_weight && (norm->rstd || norm->rstd_ext), BLADE_ERR_ARG,
+                  "qk_norm weights / scratch missing");
     BLADE_REQUIRE((reinterpret_cast<uintptr_t>(norm->q_weight) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(norm->k_weight) & 15) == 0,
                   BLADE_ERR_ALIGN, "qk_norm weights not 16B aligned");
-    const int64_t rows = B * S;
-    const unsigned sgrid = static_cast<unsigned>(ceil_div(rows, 8));
-    if (bf)
-      rms_stat_kernel<true><<<sgrid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
-                                                       static_cast<int>(S), rows, static_cast<int>(H * D), norm->eps,
-                                                       norm->rstd);
-    else
-      rms_stat_kernel<false><<<sgrid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
-                                                        static_cast<int>(S), rows, static_cast<int>(H * D), norm->eps,
-                                                        norm->rstd);
-    BLADE_CUDA_OK(cudaGetLastError());
-    rstd = norm->rstd;
+    if (!norm->rstd_ext)
+      if (int e = rms_stat_impl(q, k, norm->eps, norm->rstd, stream)) return e;
+    rstd = norm->rstd_ext ? norm->rstd_ext : norm->rstd;
     wq = static_cast<const uint16_t*>(norm->q_weight);
     wk = static_cast<const uint16_t*>(norm->k_weight);
     norm_kind = norm->kind;
@@ -737,7 +756,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
                                                               static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
                                                               static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
                                                               static_cast<int>(S), static_cast<int>(H), nb, block_size, \
-                                                              rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind)
+                                                              rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row)
 #define LAUNCH_PREP_D(DD)                                                                                             \
   do {                                                                                                                \
     if (rope_cos_sin) {                                                                                               \

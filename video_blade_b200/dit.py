@@ -28,30 +28,65 @@ from .ulysses import UlyssesGroup
 
 
 class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
-    """WanAttnProcessor2_0 (MW:75-148) with the Ulysses exchange around `inner_attention`."""
+    """WanAttnProcessor2_0 (MW:75-148) with the Ulysses exchange around `inner_attention`.
 
-    def __init__(self, group: Optional[UlyssesGroup]):
+    Fused path (default): q, k, v leave the projections untouched; only the RMSNorm statistic (one float per token
+    and tensor) is computed on the token shard and all-gathered, the raw projections travel in ONE all_to_all, and
+    the normalisation (my heads' weight slice), the rotary embedding and the curve-order gather all happen inside the
+    gather kernel, reading the packed receive buffer in place."""
+
+    def __init__(self, group: Optional[UlyssesGroup], fuse: bool = True):
         super().__init__()
         self.group = group
+        self.fuse = fuse
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
         if self.group is None or self.group.P == 1:
             return super().__call__(attn, hidden_states, encoder_hidden_states, attention_mask, rotary_emb)
+        import torch.distributed as dist
+        from .modify_wan import _norm_fusable, _rope_table
+        g = self.group
         B = hidden_states.shape[0]
-        q = attn.norm_q(attn.to_q(hidden_states)).unflatten(2, (attn.heads, -1))      # [B, S/P, H, D]
-        k = attn.norm_k(attn.to_k(hidden_states)).unflatten(2, (attn.heads, -1))
+        q = attn.to_q(hidden_states).unflatten(2, (attn.heads, -1))                    # [B, S/P, H, D]
+        k = attn.to_k(hidden_states).unflatten(2, (attn.heads, -1))
         v = attn.to_v(hidden_states).unflatten(2, (attn.heads, -1))
-        if rotary_emb is not None:                                                     # local tokens' freqs
-            q = apply_rotary_emb(q.transpose(1, 2), rotary_emb).transpose(1, 2)
-            k = apply_rotary_emb(k.transpose(1, 2), rotary_emb).transpose(1, 2)
+        fused = self.fuse and rotary_emb is not None and _norm_fusable(attn, q.flatten(2, 3), True) \
+            and getattr(attn.inner_attention, "supports_fused_rope", False)
+        if not fused:
+            q = attn.norm_q(q.flatten(2, 3)).unflatten(2, (attn.heads, -1))
+            k = attn.norm_k(k.flatten(2, 3)).unflatten(2, (attn.heads, -1))
+            if rotary_emb is not None:                                                 # local tokens' freqs
+                q = apply_rotary_emb(q.transpose(1, 2), rotary_emb).transpose(1, 2)
+                k = apply_rotary_emb(k.transpose(1, 2), rotary_emb).transpose(1, 2)
         outs = []
         for b in range(B):                                                             # exchange is per sequence
-            gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
-                                                                     v[b:b + 1].contiguous())   # one all_to_all
-            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow)                    # [1, H/P, S, D]
+            qb, kb, vb = q[b:b + 1].contiguous(), k[b:b + 1].contiguous(), v[b:b + 1].contiguous()
+            kw = {}
+            if fused:
+                from . import wanx_blocksparseattn as W
+                eng = W._engine(use_rearrange=bool(attn.inner_attention.use_rearrange))
+                stat = eng.qk_rms_stat(qb.transpose(1, 2), kb.transpose(1, 2), attn.norm_q.eps)   # [2, S/P]
+                parts = torch.empty(g.P, 2, stat.shape[1], dtype=stat.dtype, device=stat.device)
+                dist.all_gather_into_tensor(parts, stat, group=g.group)
+                rstd = parts.permute(1, 0, 2).reshape(2, -1).contiguous()              # [2, S] by token
+                Hl = attn.heads // g.P
+                D = q.shape[-1]
+                sl = slice(g.rank_in_group * Hl * D, (g.rank_in_group + 1) * Hl * D)   # my heads' weights
+                kw = dict(rotary=(_rope_table(self._full_rope(rotary_emb)), 0),
+                          qk_norm=(1, attn.norm_q.weight.detach()[sl], attn.norm_k.weight.detach()[sl],
+                                   float(attn.norm_q.eps), rstd))
+            gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(qb, kb, vb)       # one all_to_all
+            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow, **kw)              # [1, H/P, S, D]
             outs.append(self.group.gather_heads(o.transpose(1, 2)))                    # [1, S/P, H, D]
         o = torch.cat(outs, 0).flatten(2, 3).type_as(hidden_states)
         return attn.to_out[1](attn.to_out[0](o))
+
+    def _full_rope(self, rotary_local):
+        """The fused path rotates inside the gather kernel, which sees ALL tokens: it needs the full-sequence table.
+        The model hands the processor its shard; `full_rotary_emb` is attached by WanLikeDiT.forward."""
+        full = getattr(self, "full_rotary_emb", None)
+        assert full is not None, "sequence-parallel fused rotary embedding needs the full-sequence table"
+        return full
 
 
 class UlyssesCogAttnProcessor:
@@ -187,6 +222,8 @@ class WanLikeDiT(nn.Module):
         g = self.group
         if g is not None and g.P > 1:                          # keep my S/P token shard
             sl = slice(g.rank_in_group * (S // g.P), (g.rank_in_group + 1) * (S // g.P))
+            for blk in self.blocks:                            # the fused gather rotates all tokens of my heads
+                blk.attn1.get_processor().full_rotary_emb = rope
             x, rope = x[:, sl], rope[:, :, sl]
         x = self.patch_embedding(x)
         temb = self.time_embedding(self.timestep_embedding(timestep).type_as(x))
