@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) rms_stat_kernel(const uint16_t* __restric
 // ------------------------------------------------------------------------------------------------
 // prep: grid (nb, H, B), 256 threads.  One CTA = one block of `block` output rows of one head.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool IS_BF16, bool COPY, bool ROPE>
-__global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+template <int D, bool IS_BF16, bool COPY, bool ROPE, bool NORM>
+__global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
                                                          const uint16_t* __restrict__ v, Strides3 sq, Strides3 sk,
                                                          Strides3 sv, const int32_t* __restrict__ src_row,
                                                          uint16_t* __restrict__ q_r, uint16_t* __restrict__ k_r,
@@ -145,10 +145,10 @@ __global__ void __launch_bounds__(256) prep_block_kernel(const uint16_t* __restr
         rows[u] = r;
         const int rc = r < S ? r : S - 1;  // replicate padding (W:35)
         const int sr = src_row ? __ldg(src_row + rc) : rc;
-        srcs[u] = tok_row ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
+        srcs[u] = ((ROPE || NORM) && tok_row) ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
         if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
       }
-      if (rstd != nullptr && t < 2) {
+      if (NORM && t < 2) {
         // q/k RMSNorm of the processor (MW:99-102), statistic from rms_stat_kernel; weights of this head's columns
         float w[8];
         unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>((t == 0 ? wq : wk) + h * D) + chunk), w);
@@ -751,24 +751,26 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   }
   if ((parts & 1) && (q_mean || k_mean || copy)) {
     dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
-#define LAUNCH_PREP(DD, BF, CP, RP)                                                                               \
-  prep_block_kernel<DD, BF, CP, RP><<<grid, 256, 0, stream>>>(qp, kp, vp, sq, sk, sv, src_row,                        \
-                                                              static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r), \
-                                                              static_cast<uint16_t*>(v_r), q_mean, k_mean,            \
-                                                              static_cast<int>(S), static_cast<int>(H), nb, block_size, \
-                                                              rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row)
+#define LAUNCH_PREP(DD, BF, CP, RP, NM)                                                                               \
+  prep_block_kernel<DD, BF, CP, RP, NM><<<grid, 256, 0, stream>>>(                                                    \
+      qp, kp, vp, sq, sk, sv, src_row, static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r),                      \
+      static_cast<uint16_t*>(v_r), q_mean, k_mean, static_cast<int>(S), static_cast<int>(H), nb, block_size,          \
+      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row)
+#define LAUNCH_PREP_B(DD, CP, RP, NM)                                                                                 \
+  do {                                                                                                                \
+    if (bf) LAUNCH_PREP(DD, true, CP, RP, NM); else LAUNCH_PREP(DD, false, CP, RP, NM);                               \
+  } while (0)
 #define LAUNCH_PREP_D(DD)                                                                                             \
   do {                                                                                                                \
-    if (rope_cos_sin) {                                                                                               \
-      if (bf) LAUNCH_PREP(DD, true, true, true); else LAUNCH_PREP(DD, false, true, true);                             \
-    } else if (copy) {                                                                                                \
-      if (bf) LAUNCH_PREP(DD, true, true, false); else LAUNCH_PREP(DD, false, true, false);                           \
-    } else {                                                                                                          \
-      if (bf) LAUNCH_PREP(DD, true, false, false); else LAUNCH_PREP(DD, false, false, false);                         \
-    }                                                                                                                 \
+    if (rstd && rope_cos_sin) LAUNCH_PREP_B(DD, true, true, true);                                                    \
+    else if (rstd) LAUNCH_PREP_B(DD, true, false, true);                                                              \
+    else if (rope_cos_sin) LAUNCH_PREP_B(DD, true, true, false);                                                      \
+    else if (copy) LAUNCH_PREP_B(DD, true, false, false);                                                             \
+    else LAUNCH_PREP_B(DD, false, false, false);                                                                      \
   } while (0)
     if (D == 128) LAUNCH_PREP_D(128); else LAUNCH_PREP_D(64);
 #undef LAUNCH_PREP_D
+#undef LAUNCH_PREP_B
 #undef LAUNCH_PREP
     BLADE_CUDA_OK(cudaGetLastError());
   }
