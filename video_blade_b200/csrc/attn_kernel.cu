@@ -63,6 +63,13 @@ constexpr int kRegsSoftmax = 224;      // setmaxnreg split: 8 softmax warps x 22
 constexpr int kRegsOther = 56;
 constexpr int kMaxListSmem = 128;       // per-stream block ids cached in smem by the producer (longer lists: __ldg)
 constexpr float kLn2 = 0.69314718055994530942f;
+#ifndef BLADE_KV_HINT
+#define BLADE_KV_HINT kEvictLast  // K/V tiles are re-read by every query tile of the head
+#endif
+#ifndef BLADE_SOLO_NUM
+#define BLADE_SOLO_NUM 1        // dynamic queue: the last G * NUM / DEN pairs run as solo tiles
+#define BLADE_SOLO_DEN 2
+#endif
 constexpr int kItemSlots = 4;          // depth of the per-CTA item queue
 constexpr int kSchedBytes = 256;       // head of the attention workspace: the global item counter
 
@@ -386,7 +393,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int dh = 0; dh < kSub; ++dh)
             tma_load_4d(sKV + slot * kTileBytes + dh * (kBlockN * 128), map, &mz->kv_full[slot], dh * 64, row, h, b,
-                        kEvictLast);
+                        BLADE_KV_HINT);
         }
         __syncwarp();
         if (++slot == kStages) {
@@ -983,7 +990,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
     if (!no_split) {
       const int r = np % G;
       if (np < G) split = 2 * np <= G ? np : 0;
-      else if (p.sched) split = G / 2;
+      else if (p.sched) split = (G * BLADE_SOLO_NUM / BLADE_SOLO_DEN) < np ? G * BLADE_SOLO_NUM / BLADE_SOLO_DEN : np;
       else split = (r > 0 && 2 * r <= G) ? r : 0;
     }
     p.num_pair_items = np - split;
