@@ -67,7 +67,10 @@ typedef struct BladeTensor {
  * `attn.norm_k(key)` between the projections and the head split; Wan2.1 uses RMSNorm over all heads' channels).
  * kind 1: y = x * rsqrt(mean_c(x^2) + eps) * w in fp32, rounded once to the tensor dtype;
  * kind 2: diffusers' RMSNorm rounding: (x * rstd) -> tensor dtype, then * w -> tensor dtype.
- * q and k must be token-major ([B,S,H*D] memory: stride_h == D, stride_s == H*D); weights [H*D] in the tensor dtype. */
+ * q and k must be token-major ([B,S,H*D] memory: stride_h == D, stride_s == H*D); weights [H*D] in the tensor dtype.
+ * kind 3: LayerNorm over the D channels of every head (CogVideoX, MC:54-57: `attn.norm_q(query)` after the head
+ * split): y = (x - mean) * rsqrt(var + eps) * w + b in fp32, rounded once; weights / biases [D] in the tensor dtype
+ * (bias pointers may be NULL); any q/k strides. */
 typedef struct BladeQkNorm {
   int32_t kind;          /* 0 = none */
   float eps;
@@ -76,6 +79,8 @@ typedef struct BladeQkNorm {
   const float* rstd;     /* optional device fp32 [2][B*S] (q then k), indexed by TOKEN: a statistic computed elsewhere
                             (blade_qk_rms_stat on the token shard + all-gather, when the heads are sharded); NULL =
                             computed here, which needs token-major q/k */
+  const void* q_bias;    /* kind 3 only, device or NULL */
+  const void* k_bias;
 } BladeQkNorm;
 
 /* Knobs of the reference module (W:9-16, C:9-16 and the literals W:62,325,341). */

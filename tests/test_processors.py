@@ -149,3 +149,42 @@ def test_wan_processor_fused_qk_norm_matches_torch_norm():
         assert rel < 1e-2, rel
     finally:
         W.width, W.height, W.depth = old
+
+
+@pytest.mark.gpu
+def test_cog_processor_fused_layernorm_matches_torch_norm():
+    """Per-head LayerNorm of q/k (MC:54-57) inside the gather kernel == the modules' own forward followed by the
+    unfused-norm path (all blocks retained, so only the normalisation arithmetic differs)."""
+    import torch
+    from video_blade_b200 import cogvideo_blocksparseattn as Cg
+    from video_blade_b200.modify_wan import Attention
+    from video_blade_b200.modify_cogvideo import SageAttnCogVideoXAttnProcessor
+    from video_blade_b200.dit import rope_cos_sin
+    torch.manual_seed(0)
+    old = (Cg.width, Cg.height, Cg.depth, Cg.text_length, Cg.max_retain_ratio, Cg.min_retain_ratio)
+    Cg.width, Cg.height, Cg.depth, Cg.text_length = 15, 10, 6, 40
+    Cg.max_retain_ratio = Cg.min_retain_ratio = 1.0
+    try:
+        Sv, T, dim, heads = 15 * 10 * 6, 40, 192, 3
+        attn = Attention(dim, heads, qk_norm="layer_norm").cuda().to(torch.bfloat16)
+        with torch.no_grad():
+            for n in (attn.norm_q, attn.norm_k):
+                n.weight.copy_(1 + 0.3 * torch.randn(dim // heads))
+                n.bias.copy_(0.2 * torch.randn(dim // heads))
+        inner = Cg.AdaptiveBlockSparseAttnTrain()
+        inner.print_every = 0
+        attn.inner_attention = inner
+        x = torch.randn(2, Sv, dim, device="cuda", dtype=torch.bfloat16)
+        txt = torch.randn(2, T, dim, device="cuda", dtype=torch.bfloat16)
+        rope = rope_cos_sin(6, 10, 15, dim // heads, device="cuda")
+        outs = []
+        for fuse in (False, True):
+            attn.set_processor(SageAttnCogVideoXAttnProcessor(0, fuse_norm=fuse))
+            with torch.no_grad():
+                hv, ht = attn(x, encoder_hidden_states=txt, image_rotary_emb=rope)
+            outs.append(torch.cat([ht, hv], 1).float())
+        d = outs[1] - outs[0]
+        rel = float(d.norm() / outs[0].norm())
+        assert rel < 1e-2, rel
+    finally:
+        Cg.width, Cg.height, Cg.depth, Cg.text_length, Cg.max_retain_ratio, Cg.min_retain_ratio = old

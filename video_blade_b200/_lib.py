@@ -22,7 +22,7 @@ class BladeTensor(C.Structure):
 
 class BladeQkNorm(C.Structure):
     _fields_ = [("kind", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p),
-                ("rstd", C.c_void_p)]
+                ("rstd", C.c_void_p), ("q_bias", C.c_void_p), ("k_bias", C.c_void_p)]
 
 
 class BladeAsaConfig(C.Structure):

@@ -346,14 +346,21 @@ class AsaEngine:
         if qk_norm is not None:
             kind, wq, wk, eps = qk_norm[:4]
             rstd = qk_norm[4] if len(qk_norm) > 4 else None      # statistic computed elsewhere, fp32 [2, B*S] by token
-            if virtual_rows is not None and rstd is None:
+            bq, bk = (qk_norm[5], qk_norm[6]) if len(qk_norm) > 6 else (None, None)   # kind 3: LayerNorm biases
+            per_head = int(kind) == 3
+            if virtual_rows is not None and rstd is None and not per_head:
                 raise ValueError("fused q/k norm on the packed Ulysses layout needs the statistic (qk_rms_stat)")
-            assert wq.dtype == q.dtype and wk.dtype == q.dtype and wq.numel() == H * D and wk.numel() == H * D
+            n_w = D if per_head else H * D
+            assert wq.dtype == q.dtype and wk.dtype == q.dtype and wq.numel() == n_w and wk.numel() == n_w
             wq, wk = wq.contiguous(), wk.contiguous()
             if rstd is not None:
                 assert rstd.dtype == torch.float32 and rstd.is_contiguous() and rstd.numel() == 2 * B * S
-            norm_keep = BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr(), ptr(rstd))
-            cfg.qk_norm = C.pointer(norm_keep)
+            if bq is not None:
+                assert bq.dtype == q.dtype and bk.dtype == q.dtype and bq.numel() == D and bk.numel() == D
+                bq, bk = bq.contiguous(), bk.contiguous()
+            norm_keep = (BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr(), ptr(rstd), ptr(bq), ptr(bk)),
+                         wq, wk, bq, bk)
+            cfg.qk_norm = C.pointer(norm_keep[0])
         if rope is not None:
             table, first = rope
             assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[-2:] == (D // 2, 2)

@@ -158,16 +158,17 @@ class AdaptiveBlockSparseAttnTrain(nn.Module):
         self._cnt_den = 0
         self.print_every = 800
 
-    supports_fused_rope = True   # processors may hand over un-rotated q/k plus the rotary table
+    supports_fused_rope = True
+    supports_fused_qk_norm = True  # per-head LayerNorm of q/k (MC:54-57) inside the gather kernel   # processors may hand over un-rotated q/k plus the rotary table
 
-    def forward(self, q, k, v, virtual_rows=None, rotary=None):
+    def forward(self, q, k, v, virtual_rows=None, rotary=None, qk_norm=None):
         """`virtual_rows` (optional, int32 [S]): q/k/v are strided views into a packed Ulysses receive buffer and
         token s lives at row virtual_rows[s] (video_blade_b200.ulysses.scatter_heads_fused).
         `rotary` (optional): (fp32 table [rows, D/2, 2] of (cos, sin), first_row) -- the processor's rotary
         embedding (MW:108-116 / MC:59-64) is then applied to q and k inside the gather kernel."""
         m = sys.modules[__name__]
         eng = _engine(use_rearrange=bool(self.use_rearrange))
-        out, cnt = eng.forward(q, k, v, virtual_rows=virtual_rows, rope=rotary)
+        out, cnt = eng.forward(q, k, v, virtual_rows=virtual_rows, rope=rotary, qk_norm=qk_norm)
         # sparsity bookkeeping without the reference's per-layer .item() sync (W:398): accumulate on device
         if self._cnt_acc is None or self._cnt_acc.device != cnt.device:
             self._cnt_acc = torch.zeros((), dtype=torch.float64, device=cnt.device)

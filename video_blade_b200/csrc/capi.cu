@@ -227,6 +227,8 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     pn.k_weight = cfg->qk_norm->k_weight;
     pn.rstd = reinterpret_cast<float*>(ws + w.rstd);
     pn.rstd_ext = cfg->qk_norm->rstd;
+    pn.q_bias = cfg->qk_norm->q_bias;
+    pn.k_bias = cfg->qk_norm->k_bias;
   }
   float* q_mean = reinterpret_cast<float*>(ws + w.q_mean);
   float* k_mean = reinterpret_cast<float*>(ws + w.k_mean);

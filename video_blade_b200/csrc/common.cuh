@@ -56,6 +56,8 @@ struct PrepNorm {
   const void* k_weight;
   float* rstd;            // scratch the statistic kernel fills ...
   const float* rstd_ext;  // ... unless the caller brings the statistic (indexed by token)
+  const void* q_bias;     // kind 3 (per-head LayerNorm) only
+  const void* k_bias;
 };
 int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,

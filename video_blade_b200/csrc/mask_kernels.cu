@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
                                                          const float* __restrict__ rope, int rope_first,
                                                          const float* __restrict__ rstd, const uint16_t* __restrict__ wq,
                                                          const uint16_t* __restrict__ wk, int norm_kind,
-                                                         const int32_t* __restrict__ tok_row) {
+                                                         const int32_t* __restrict__ tok_row,
+                                                         const uint16_t* __restrict__ bq, const uint16_t* __restrict__ bk,
+                                                         float norm_eps) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -148,7 +150,42 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
         srcs[u] = ((ROPE || NORM) && tok_row) ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
         if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
       }
-      if (NORM && t < 2) {
+      if (NORM && t < 2 && norm_kind == 3) {
+        // CogVideoX: LayerNorm over the D channels of this head (MC:54-57); a row is spread over LPR lanes
+        float w[8], bias[8];
+        unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>(t == 0 ? wq : wk) + chunk), w);
+        const uint16_t* bp = t == 0 ? bq : bk;
+        if (bp) {
+          unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>(bp) + chunk), bias);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bias[i] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (p0 + u >= passes) continue;  // warp-uniform
+          float f[8];
+          unpack8<IS_BF16>(val[u], f);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum += f[i];
+#pragma unroll
+          for (int off = LPR / 2; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+          const float mean = sum * (1.0f / D);
+          float var = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i] -= mean;
+            var = fmaf(f[i], f[i], var);
+          }
+#pragma unroll
+          for (int off = LPR / 2; off; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+          const float r = rsqrtf(var * (1.0f / D) + norm_eps);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] * r, w[i], bias[i]);
+          val[u] = pack8<IS_BF16>(f);
+        }
+      } else if (NORM && t < 2) {
         // q/k RMSNorm of the processor (MW:99-102), statistic from rms_stat_kernel; weights of this head's columns
         float w[8];
         unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>((t == 0 ? wq : wk) + h * D) + chunk), w);
@@ -732,21 +769,27 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
   const float* rstd = nullptr;
-  const uint16_t *wq = nullptr, *wk = nullptr;
+  const uint16_t *wq = nullptr, *wk = nullptr, *bq = nullptr, *bk = nullptr;
   int norm_kind = 0;
+  float norm_eps = 0.f;
   if (norm && norm->kind != 0 && (parts & 1)) {
-    BLADE_REQUIRE(norm->kind == 1 || norm->kind == 2, BLADE_ERR_ARG, "qk_norm kind %d not in {1,2}", norm->kind);
+    BLADE_REQUIRE(norm->kind >= 1 && norm->kind <= 3, BLADE_ERR_ARG, "qk_norm kind %d not in {1,2,3}", norm->kind);
     BLADE_REQUIRE(copy, BLADE_ERR_ARG, "qk_norm needs the q_r/k_r/v_r outputs");
-    BLADE_REQUIRE(norm->q_weight && norm->k_weight && (norm->rstd || norm->rstd_ext), BLADE_ERR_ARG,
+    BLADE_REQUIRE(norm->q_weight && norm->k_weight && (norm->kind == 3 || norm->rstd || norm->rstd_ext), BLADE_ERR_ARG,
                   "qk_norm weights / scratch missing");
     BLADE_REQUIRE((reinterpret_cast<uintptr_t>(norm->q_weight) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(norm->k_weight) & 15) == 0,
                   BLADE_ERR_ALIGN, "qk_norm weights not 16B aligned");
-    if (!norm->rstd_ext)
-      if (int e = rms_stat_impl(q, k, norm->eps, norm->rstd, stream)) return e;
-    rstd = norm->rstd_ext ? norm->rstd_ext : norm->rstd;
+    if (norm->kind != 3) {
+      if (!norm->rstd_ext)
+        if (int e = rms_stat_impl(q, k, norm->eps, norm->rstd, stream)) return e;
+      rstd = norm->rstd_ext ? norm->rstd_ext : norm->rstd;
+    }
     wq = static_cast<const uint16_t*>(norm->q_weight);
     wk = static_cast<const uint16_t*>(norm->k_weight);
+    bq = static_cast<const uint16_t*>(norm->q_bias);
+    bk = static_cast<const uint16_t*>(norm->k_bias);
+    norm_eps = norm->eps;
     norm_kind = norm->kind;
   }
   if ((parts & 1) && (q_mean || k_mean || copy)) {
@@ -755,15 +798,15 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   prep_block_kernel<DD, BF, CP, RP, NM><<<grid, 256, 0, stream>>>(                                                    \
       qp, kp, vp, sq, sk, sv, src_row, static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r),                      \
       static_cast<uint16_t*>(v_r), q_mean, k_mean, static_cast<int>(S), static_cast<int>(H), nb, block_size,          \
-      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row)
+      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps)
 #define LAUNCH_PREP_B(DD, CP, RP, NM)                                                                                 \
   do {                                                                                                                \
     if (bf) LAUNCH_PREP(DD, true, CP, RP, NM); else LAUNCH_PREP(DD, false, CP, RP, NM);                               \
   } while (0)
 #define LAUNCH_PREP_D(DD)                                                                                             \
   do {                                                                                                                \
-    if (rstd && rope_cos_sin) LAUNCH_PREP_B(DD, true, true, true);                                                    \
-    else if (rstd) LAUNCH_PREP_B(DD, true, false, true);                                                              \
+    if (norm_kind && rope_cos_sin) LAUNCH_PREP_B(DD, true, true, true);                                               \
+    else if (norm_kind) LAUNCH_PREP_B(DD, true, false, true);                                                         \
     else if (rope_cos_sin) LAUNCH_PREP_B(DD, true, true, false);                                                      \
     else if (copy) LAUNCH_PREP_B(DD, true, false, false);                                                             \
     else LAUNCH_PREP_B(DD, false, false, false);                                                                      \

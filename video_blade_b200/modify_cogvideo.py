@@ -26,9 +26,10 @@ def apply_rotary_emb(x: torch.Tensor, freqs_cis) -> torch.Tensor:
 class SageAttnCogVideoXAttnProcessor:
     """MC:11-76."""
 
-    def __init__(self, idx, fuse_rope: bool = True):
+    def __init__(self, idx, fuse_rope: bool = True, fuse_norm: bool = True):
         self.idx = idx
         self.fuse_rope = fuse_rope
+        self.fuse_norm = fuse_norm      # per-head LayerNorm of q/k inside the gather kernel
         self._table = None
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor,
@@ -46,10 +47,18 @@ class SageAttnCogVideoXAttnProcessor:
         query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
         key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
         value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
-        if attn.norm_q is not None:
-            query = attn.norm_q(query).to(dtype=value.dtype)
-        if attn.norm_k is not None:
-            key = attn.norm_k(key).to(dtype=value.dtype)
+        fused_norm = None
+        # the norm precedes the rotary embedding (MC:54-64): it may only move into the kernel if the rotation does too
+        rope_in_kernel = image_rotary_emb is None or (self.fuse_rope and not attn.is_cross_attention)
+        if self.fuse_norm and rope_in_kernel and _norm_fusable(attn, query, head_dim):
+            nq, nk = attn.norm_q, attn.norm_k
+            fused_norm = (3, nq.weight.detach(), nk.weight.detach(), float(nq.eps), None,
+                          None if nq.bias is None else nq.bias.detach(), None if nk.bias is None else nk.bias.detach())
+        else:
+            if attn.norm_q is not None:
+                query = attn.norm_q(query).to(dtype=value.dtype)
+            if attn.norm_k is not None:
+                key = attn.norm_k(key).to(dtype=value.dtype)
         fused_rope = None
         if image_rotary_emb is not None:                                       # MC:59-64
             if getattr(attn.inner_attention, "supports_fused_rope", False) and not attn.is_cross_attention \
@@ -64,8 +73,13 @@ class SageAttnCogVideoXAttnProcessor:
                 query[:, :, text_seq_length:] = apply_rotary_emb(query[:, :, text_seq_length:], image_rotary_emb)
                 if not attn.is_cross_attention:
                     key[:, :, text_seq_length:] = apply_rotary_emb(key[:, :, text_seq_length:], image_rotary_emb)
-        if fused_rope is not None:
-            hidden_states = attn.inner_attention(query, key, value, rotary=fused_rope)
+        if fused_rope is not None or fused_norm is not None:
+            kw = {}
+            if fused_rope is not None:
+                kw["rotary"] = fused_rope
+            if fused_norm is not None:
+                kw["qk_norm"] = fused_norm
+            hidden_states = attn.inner_attention(query, key, value, **kw)
         else:
             hidden_states = attn.inner_attention(query, key, value)            # MC:65 (no .contiguous() needed)
         hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim)
@@ -74,6 +88,22 @@ class SageAttnCogVideoXAttnProcessor:
         encoder_hidden_states, hidden_states = hidden_states.split(
             [text_seq_length, hidden_states.size(1) - text_seq_length], dim=1)
         return hidden_states, encoder_hidden_states
+
+
+def _norm_fusable(attn, query, head_dim: int) -> bool:
+    """Fused path: both norms are LayerNorm over the head dimension with parameters in the activation dtype, on a
+    self-attention layer; the rotary embedding then has to be fused too (the norm comes first, MC:54-64)."""
+    nq, nk = getattr(attn, "norm_q", None), getattr(attn, "norm_k", None)
+    if nq is None or nk is None or getattr(attn, "is_cross_attention", False) or not query.is_cuda:
+        return False
+    if not getattr(attn.inner_attention, "supports_fused_qk_norm", False) \
+            or not getattr(attn.inner_attention, "supports_fused_rope", False):
+        return False
+    for n in (nq, nk):
+        if not isinstance(n, torch.nn.LayerNorm) or tuple(n.normalized_shape) != (head_dim,) or n.weight is None \
+                or n.weight.dtype != query.dtype or (n.bias is not None and n.bias.dtype != query.dtype):
+            return False
+    return True
 
 
 def set_block_sparse_attn_cogvideox(model, verbose=False):

@@ -61,7 +61,10 @@ class WanAttnProcessor2_0:
         key = attn.to_k(encoder_hidden_states)
         value = attn.to_v(encoder_hidden_states)
         fused_norm = None
-        if self.fuse_norm and _norm_fusable(attn, query, encoder_hidden_states is hidden_states):
+        # the norm precedes the rotary embedding (MW:99-116): it may only move into the kernel if the rotation does too
+        rope_in_kernel = rotary_emb is None or (self.fuse_rope and getattr(attn.inner_attention, "supports_fused_rope", False)
+                                                and getattr(attn, "add_k_proj", None) is None and hidden_states.is_cuda)
+        if self.fuse_norm and rope_in_kernel and _norm_fusable(attn, query, encoder_hidden_states is hidden_states):
             nq, nk = attn.norm_q, attn.norm_k
             fused_norm = (2 if getattr(nq, "_two_roundings", False) else 1, nq.weight.detach(), nk.weight.detach(),
                           float(nq.eps))
