@@ -94,24 +94,39 @@ class UlyssesCogAttnProcessor:
     the Ulysses exchange around `inner_attention`.  `rope_local` = (cos, sin) [S/P, D] for my tokens, identity rows
     for text tokens (MC:59-64 rotates the video part only)."""
 
-    def __init__(self, group: UlyssesGroup):
+    def __init__(self, group: UlyssesGroup, fuse: bool = True):
         self.group = group
+        self.fuse = fuse
+        self._table = None
 
-    def __call__(self, attn, hidden_states, rope_local):
-        from .modify_cogvideo import apply_rotary_emb as cog_rope
+    def __call__(self, attn, hidden_states, rope_local, rope_full=None, text_len=0):
+        from .modify_cogvideo import _norm_fusable, apply_rotary_emb as cog_rope
         B, Sl, _ = hidden_states.shape
         q = attn.to_q(hidden_states).view(B, Sl, attn.heads, -1)
         k = attn.to_k(hidden_states).view(B, Sl, attn.heads, -1)
         v = attn.to_v(hidden_states).view(B, Sl, attn.heads, -1)
-        q = attn.norm_q(q).to(v.dtype)                                                 # LayerNorm per head (MC:54-57)
-        k = attn.norm_k(k).to(v.dtype)
-        q = cog_rope(q.transpose(1, 2), rope_local).transpose(1, 2)
-        k = cog_rope(k.transpose(1, 2), rope_local).transpose(1, 2)
+        kw = {}
+        if self.fuse and rope_full is not None and _norm_fusable(attn, q, q.shape[-1]):
+            # per-head LayerNorm and the rotary embedding need nothing from other ranks: both run inside the gather
+            # kernel on the packed receive buffer (my heads, all tokens); the projections travel untouched
+            cos, sin = rope_full
+            key_ = (cos.data_ptr(), sin.data_ptr())
+            if self._table is None or self._table[0] != key_:
+                self._table = (key_, torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(q.device, torch.float32).contiguous())
+            nq, nk = attn.norm_q, attn.norm_k
+            kw = dict(rotary=(self._table[1], int(text_len)),
+                      qk_norm=(3, nq.weight.detach(), nk.weight.detach(), float(nq.eps), None,
+                               None if nq.bias is None else nq.bias.detach(), None if nk.bias is None else nk.bias.detach()))
+        else:
+            q = attn.norm_q(q).to(v.dtype)                                             # LayerNorm per head (MC:54-57)
+            k = attn.norm_k(k).to(v.dtype)
+            q = cog_rope(q.transpose(1, 2), rope_local).transpose(1, 2)
+            k = cog_rope(k.transpose(1, 2), rope_local).transpose(1, 2)
         outs = []
         for b in range(B):                                                             # exchange is per sequence
             gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(q[b:b + 1].contiguous(), k[b:b + 1].contiguous(),
                                                                      v[b:b + 1].contiguous())
-            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow)                    # [1, H/P, S, D], text first
+            o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow, **kw)              # [1, H/P, S, D], text first
             outs.append(self.group.gather_heads(o.transpose(1, 2)))                    # [1, S/P, H, D]
         o = torch.cat(outs, 0).flatten(2, 3).type_as(hidden_states)
         return attn.to_out[1](attn.to_out[0](o))
@@ -371,7 +386,8 @@ class CogLikeDiT(nn.Module):
         sin_f = torch.cat([torch.zeros(T, D, device=sin.device), sin])[sl]
         proc = UlyssesCogAttnProcessor(g)
         for blk in self.transformer_blocks:
-            for norm, fn in ((blk.norm1, lambda h, a=blk.attn1: proc(a, h, (cos_f, sin_f))), (blk.norm2, blk.ff)):
+            for norm, fn in ((blk.norm1, lambda h, a=blk.attn1: proc(a, h, (cos_f, sin_f), rope_full=rope, text_len=T)),
+                             (blk.norm2, blk.ff)):
                 sh, sc, gt, tsh, tsc, tg = norm.linear(F.silu(temb)).chunk(6, dim=1)
                 shift = torch.where(is_text, tsh[:, None], sh[:, None])
                 scale = torch.where(is_text, tsc[:, None], sc[:, None])
