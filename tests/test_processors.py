@@ -188,3 +188,19 @@ def test_cog_processor_fused_layernorm_matches_torch_norm():
         assert rel < 1e-2, rel
     finally:
         Cg.width, Cg.height, Cg.depth, Cg.text_length, Cg.max_retain_ratio, Cg.min_retain_ratio = old
+
+
+def test_norm_fusion_is_only_claimed_for_known_modules():
+    """The fused q/k norm reproduces a specific module's rounding; unknown normalisation modules stay on torch."""
+    import torch
+    from video_blade_b200.modify_wan import RMSNorm, _rms_kind
+    assert _rms_kind(RMSNorm(8)) == 1
+    assert _rms_kind(torch.nn.LayerNorm(8)) == 0
+    if hasattr(torch.nn, "RMSNorm"):
+        assert _rms_kind(torch.nn.RMSNorm(8)) == 0
+
+    class Fake(torch.nn.Module):
+        pass
+    Fake.__name__ = "RMSNorm"
+    Fake.__module__ = "diffusers.models.normalization"
+    assert _rms_kind(Fake()) == 2

@@ -44,7 +44,7 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
         if self.group is None or self.group.P == 1:
             return super().__call__(attn, hidden_states, encoder_hidden_states, attention_mask, rotary_emb)
         import torch.distributed as dist
-        from .modify_wan import _norm_fusable, _rope_table
+        from .modify_wan import _norm_fusable, _rms_kind, _rope_table
         g = self.group
         B = hidden_states.shape[0]
         q = attn.to_q(hidden_states).unflatten(2, (attn.heads, -1))                    # [B, S/P, H, D]
@@ -73,7 +73,7 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
                 D = q.shape[-1]
                 sl = slice(g.rank_in_group * Hl * D, (g.rank_in_group + 1) * Hl * D)   # my heads' weights
                 kw = dict(rotary=(_rope_table(self._full_rope(rotary_emb)), 0),
-                          qk_norm=(1, attn.norm_q.weight.detach()[sl], attn.norm_k.weight.detach()[sl],
+                          qk_norm=(_rms_kind(attn.norm_q), attn.norm_q.weight.detach()[sl], attn.norm_k.weight.detach()[sl],
                                    float(attn.norm_q.eps), rstd))
             gq, gk, gv, vrow, _keep = self.group.scatter_heads_fused(qb, kb, vb)       # one all_to_all
             o = attn.inner_attention(gq, gk, gv, virtual_rows=vrow, **kw)              # [1, H/P, S, D]

@@ -66,8 +66,7 @@ class WanAttnProcessor2_0:
                                                 and getattr(attn, "add_k_proj", None) is None and hidden_states.is_cuda)
         if self.fuse_norm and rope_in_kernel and _norm_fusable(attn, query, encoder_hidden_states is hidden_states):
             nq, nk = attn.norm_q, attn.norm_k
-            fused_norm = (2 if getattr(nq, "_two_roundings", False) else 1, nq.weight.detach(), nk.weight.detach(),
-                          float(nq.eps))
+            fused_norm = (_rms_kind(nq), nq.weight.detach(), nk.weight.detach(), float(nq.eps))
         else:
             if attn.norm_q is not None:                                        # MW:99-102
                 query = attn.norm_q(query)
@@ -122,10 +121,21 @@ def _norm_fusable(attn, query, self_attention: bool) -> bool:
         return False
     for n in (nq, nk):
         w = getattr(n, "weight", None)
-        if type(n).__name__ != "RMSNorm" or w is None or w.dtype != query.dtype or w.numel() != query.shape[-1] \
-                or getattr(n, "bias", None) is not None:
+        if _rms_kind(n) == 0 or w is None or w.dtype != query.dtype or w.numel() != query.shape[-1] \
+                or getattr(n, "bias", None) is not None or getattr(n, "eps", None) is None:
             return False
-    return True
+    return _rms_kind(nq) == _rms_kind(nk)
+
+
+def _rms_kind(n) -> int:
+    """Which rounding the module's forward has (BladeQkNorm.kind): 1 = this package's RMSNorm (fp32 chain, one
+    rounding), 2 = diffusers.models.normalization.RMSNorm with half-precision weights ((x * rstd) -> weight dtype,
+    then * weight), 0 = anything else (e.g. torch.nn.RMSNorm, whose arithmetic is different again): not fused."""
+    if isinstance(n, RMSNorm):
+        return 2 if getattr(n, "_two_roundings", False) else 1
+    if type(n).__name__ == "RMSNorm" and type(n).__module__.startswith("diffusers."):
+        return 2
+    return 0
 
 
 def set_adaptive_block_sparse_attn_wanx(model, verbose=False):
