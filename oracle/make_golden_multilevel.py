@@ -1,0 +1,92 @@
+"""TEST INFRASTRUCTURE.  Golden vectors for oracle/multilevel.py from the REFERENCE's own code, run in the build
+container (needs /root/reference; not needed on the GPU box):
+
+  * the multi-level Triton forward kernel K9 (`_forward`, BLOCK_M = BLOCK_N = POOLING_BLOCK_N = 128 as N:10
+    instantiates it) under TRITON_INTERPRET=1 on CPU, fp32 inputs;
+  * `transfer_attn_to_mask` of N (multi-level mask from block scores), whose source is executed stand-alone
+    (the module itself imports CUDA-only pieces).
+
+    python -m oracle.make_golden_multilevel      ->  tests/golden/multilevel.npz
+"""
+import ast
+import importlib.util
+import os
+import sys
+
+os.environ["TRITON_INTERPRET"] = "1"        # before triton is imported
+
+import numpy as np
+import torch
+
+REF = "/root/reference/cogvideox/sample_evaluate/Triton"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def load_k9():
+    spec = importlib.util.spec_from_file_location(
+        "k9_ref", os.path.join(REF, "kernels", "block_sparse_attn_kernel_with_backward_9_10.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.is_hip = lambda: False
+
+    class _NoDevice:                          # `with torch.cuda.device(q.device.index)` on CPU tensors
+        def __init__(self, *a):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+    torch.cuda.device = _NoDevice
+    return mod
+
+
+def load_mask_fn():
+    """transfer_attn_to_mask of N, compiled from its own source text (N:154-207), sort pinned to stable."""
+    src = open(os.path.join(REF, "cogvideo_newattn.py")).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "transfer_attn_to_mask")
+    code = compile(ast.Module(body=[fn], type_ignores=[]), "cogvideo_newattn.py", "exec")
+
+    class _Torch:                             # torch with a stable sort (the reference leaves tie order open)
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def sort(x, dim=-1, descending=False):
+            return torch.sort(x, dim=dim, descending=descending, stable=True)
+    ns = {"torch": _Torch()}
+    exec(code, ns)
+    return ns["transfer_attn_to_mask"]
+
+
+def main():
+    k9 = load_k9()
+    mask_fn = load_mask_fn()
+    out = {}
+    g = torch.Generator().manual_seed(42)
+    # ---- masks
+    for name, (B, H, n) in {"m_small": (1, 2, 16), "m_cog": (1, 2, 139)}.items():
+        attn = torch.softmax(torch.randn(B, H, n, n, generator=g) * 2, dim=-1)
+        attn[0, 0, 3, :4] = attn[0, 0, 3, 0]                      # ties
+        out[f"{name}_attn"] = attn.numpy()
+        out[f"{name}_mask"] = mask_fn(attn.clone()).numpy()
+    # ---- attention
+    cases = {"a_levels": (1, 2, 512, 64), "a_ragged": (1, 1, 300, 64), "a_d128": (1, 1, 384, 128)}
+    for name, (B, H, N, D) in cases.items():
+        q, k, v = (torch.randn(B, H, N, D, generator=g) for _ in range(3))
+        nb = -(-N // 128)
+        mask = torch.randint(0, 5, (B, H, nb, nb), generator=g)
+        mask = torch.tensor([0, 1, 2, 4, 8], dtype=torch.int32)[mask]
+        mask[..., torch.arange(nb), torch.arange(nb)] = 1         # every row attends something
+        o = k9._forward(None, q, k, v, mask.contiguous(), 1.0 / D ** 0.5, BLOCK_M=128, BLOCK_N=128, POOLING_BLOCK_N=128)
+        for key, t in (("q", q), ("k", k), ("v", v), ("mask", mask), ("o", o)):
+            out[f"{name}_{key}"] = t.numpy()
+        print(name, "ok", tuple(o.shape), float(o.abs().mean()))
+    np.savez_compressed(os.path.join(OUT, "multilevel.npz"), **out)
+    print("wrote", os.path.join(OUT, "multilevel.npz"))
+
+
+if __name__ == "__main__":
+    main()
