@@ -86,3 +86,19 @@ def test_bench_json_contract():
     assert line["roofline"]["bound"] == "tensor" and 0.2 < line["roofline"]["frac"] < 1.2
     assert line["gpu_launches"] == 3 * 5 and line["value"] > 100
     assert abs(line["config"]["algorithmic_tflop_per_step"] - 1.327) < 0.01
+
+
+def test_reference_arm_json_contract_cpu():
+    """`bench.py --impl reference` needs no GPU: the oracle port on the host cores, one bounded sample per step,
+    same metric / unit / config as the GPU arm, `e2e` repeating the line's own value with zero transfer bytes."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("ASA sparse-effective attention throughput")
+    assert "workload" in line["config"] and "32760 tok" in line["config"]["workload"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "heads" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and 0 < line["value"] < 5
