@@ -58,12 +58,14 @@ def load_mask_fn():
             return torch.sort(x, dim=dim, descending=descending, stable=True)
     ns = {"torch": _Torch()}
     exec(code, ns)
-    return ns["transfer_attn_to_mask"]
+    # the module-level `mask_ratios` the reference actually runs with (N:13-19; differs from the function's default)
+    assign = next(n for n in tree.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "mask_ratios")
+    return ns["transfer_attn_to_mask"], ast.literal_eval(assign.value)
 
 
 def main():
     k9 = load_k9()
-    mask_fn = load_mask_fn()
+    mask_fn, module_ratios = load_mask_fn()
     out = {}
     g = torch.Generator().manual_seed(42)
     # ---- masks
@@ -72,6 +74,8 @@ def main():
         attn[0, 0, 3, :4] = attn[0, 0, 3, 0]                      # ties
         out[f"{name}_attn"] = attn.numpy()
         out[f"{name}_mask"] = mask_fn(attn.clone()).numpy()
+        out[f"{name}_mask_module_ratios"] = mask_fn(attn.clone(), module_ratios).numpy()
+    out["module_ratios"] = np.array([[lv, a, b] for lv, (a, b) in module_ratios.items()], dtype=np.float64)
     # ---- attention
     cases = {"a_levels": (1, 2, 512, 64), "a_ragged": (1, 1, 300, 64), "a_d128": (1, 1, 384, 128)}
     for name, (B, H, N, D) in cases.items():

@@ -22,6 +22,10 @@ def test_multilevel_mask_bit_exact(gold, name):
     assert got.dtype == torch.int32 and torch.equal(got, want)
     assert set(np.unique(got.numpy())) <= {0, 1, 2, 4, 8}
     assert bool((got[..., -2:, :] == 1).all()) and bool((got[..., :, -2:] == 1).all())
+    # the ratios the reference module actually runs with (N:13-19): 5 % full, 10 % 2x, 10 % 4x, 25 % 8x, rest skipped
+    ratios = {int(lv): (float(a), float(b)) for lv, a, b in gold["module_ratios"]}
+    assert ratios[0] == (0.5, 1.0)
+    assert torch.equal(M.multilevel_mask(attn, ratios), torch.from_numpy(gold[f"{name}_mask_module_ratios"]))
 
 
 @pytest.mark.parametrize("name", ["a_levels", "a_ragged", "a_d128"])
