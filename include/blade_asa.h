@@ -18,6 +18,10 @@
  *   standard_attn + LSE merge + reversed_rearrange
  *                                     (W:21-24, 348-370, 154-159)         blade_asa_attn_fwd
  *   AdaptiveBlockSparseAttnTrain.forward  (W:383-408, C:405-427)         blade_asa_forward
+ *   processor steps in front of the module, optionally fused into the gather (blade_asa_forward via
+ *   BladeAsaConfig): rotary embedding (modify_wan.py:108-116 / modify_cogvideo.py:59-64) -> rope_cos_sin;
+ *   q/k normalisation (modify_wan.py:99-102 RMSNorm over all heads / modify_cogvideo.py:54-57 LayerNorm
+ *   per head) -> qk_norm (BladeQkNorm), statistic helper blade_qk_rms_stat
  *
  * Conventions
  *   - plain C, no C++/torch types; every pointer marked "device" is a CUDA device pointer owned by the
