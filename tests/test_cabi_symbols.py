@@ -98,3 +98,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_built_library_contains_blackwell_tensor_core_and_tma_code():
+    """The shipped sm_100a code really is tcgen05 / TMEM / TMA (B200_PROFILING.md lists the SASS mnemonics): the
+    attention and estimator kernels must contain UTCHMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTMALDG (TMA
+    tensor loads) and mbarrier try-waits -- not a recompiled mma.sync path."""
+    import shutil
+    import subprocess
+    from video_blade_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "SYNCS.PHASECHK"):
+        assert mnemonic in sass, mnemonic
+    for legacy in ("HMMA.", "WGMMA"):
+        assert legacy not in sass, legacy
