@@ -102,3 +102,24 @@ def test_reference_arm_json_contract_cpu():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "heads" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and 0 < line["value"] < 5
+
+
+def test_algorithmic_flops_match_baseline_formula():
+    """BASELINE.md section 3 at the headline shape: Wan 32 760 tokens, 12 heads, d = 128, 43 of 256 blocks per row
+    (the ragged last block selected on a third of the rows), 1 092 pooled keys."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    S, D, H, nb, n_pool = 32760, 128, 12, 256, 1092
+    cnt = torch.full((1, H, nb), 43)
+    last = torch.zeros(1, H, nb, dtype=torch.bool)
+    last[..., ::3] = True
+    got = bench.algorithmic_flops(cnt, last, S, D, n_pool)
+    rows = torch.full((nb,), 128.0, dtype=torch.float64)
+    rows[-1] = S - 255 * 128                                     # 120
+    cols = torch.full((nb,), 43 * 128.0, dtype=torch.float64)
+    cols[::3] -= 8                                               # the last key block holds 120 real keys
+    want = 4 * D * H * float((rows * (cols + n_pool)).sum())
+    assert abs(got - want) / want < 1e-12
+    assert abs(got / 1e12 - 1.327) < 0.005
