@@ -63,6 +63,62 @@ def load_mask_fn():
     return ns["transfer_attn_to_mask"], ast.literal_eval(assign.value)
 
 
+def golden_layer(out):
+    """The reference module N end to end on CPU: its own GilbertRearranger, random token sampling (draws recorded),
+    Triton estimator and Triton multi-level kernel under the interpreter, fp32."""
+    import importlib
+    import types
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
+    sys.path.insert(0, os.path.dirname(REF))
+    try:
+        N = importlib.import_module("Triton.cogvideo_newattn")
+    finally:
+        sys.path.remove(os.path.dirname(REF))
+    for m in list(sys.modules.values()):
+        if getattr(m, "__name__", "").startswith("Triton.kernels") and hasattr(m, "is_hip"):
+            m.is_hip = lambda: False
+    g = torch.Generator().manual_seed(7)
+    draws = []
+
+    class _Torch:                              # N's `torch`: no device='cuda', stable sort, recorded random draws
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def tensor(*a, **k):
+            k.pop("device", None)
+            return torch.tensor(*a, **k)
+
+        @staticmethod
+        def sort(*a, **k):
+            k["stable"] = True
+            return torch.sort(*a, **k)
+
+        @staticmethod
+        def rand(*shape, **k):
+            k.pop("device", None)
+            r = torch.rand(*shape, generator=g)
+            draws.append(r.clone())
+            return r
+    N.torch = _Torch()
+    grid, text = (8, 8, 8), 64
+    N.width, N.height, N.depth, N.text_length = grid[0], grid[1], grid[2], text
+    mod = N.AdaptiveBlockSparseAttnTrain()
+    B, H, D = 1, 2, 64
+    S = grid[0] * grid[1] * grid[2] + text
+    q, k, v = (torch.randn(B, H, S, D, generator=g) for _ in range(3))
+    o = mod(q, k, v)
+    assert len(draws) == 2                     # one draw for q, one for k (N:84-85), shared by all blocks
+    for key, t in (("q", q), ("k", k), ("v", v), ("o", o), ("rand_q", draws[0]), ("rand_k", draws[1])):
+        out[f"layer_{key}"] = t.numpy()
+    out["layer_grid_text"] = np.array(list(grid) + [text], dtype=np.int64)
+    out["layer_ratios"] = np.array([[lv, a, b] for lv, (a, b) in N.mask_ratios.items()], dtype=np.float64)
+    print("layer ok", tuple(o.shape), float(o.abs().mean()))
+
+
 def main():
     k9 = load_k9()
     mask_fn, module_ratios = load_mask_fn()
@@ -88,6 +144,7 @@ def main():
         for key, t in (("q", q), ("k", k), ("v", v), ("mask", mask), ("o", o)):
             out[f"{name}_{key}"] = t.numpy()
         print(name, "ok", tuple(o.shape), float(o.abs().mean()))
+    golden_layer(out)
     np.savez_compressed(os.path.join(OUT, "multilevel.npz"), **out)
     print("wrote", os.path.join(OUT, "multilevel.npz"))
 

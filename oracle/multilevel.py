@@ -108,3 +108,17 @@ def multilevel_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, leve
                 s = qi @ Kc.T * scale + bc
                 out[b, h, rows] = torch.softmax(s, dim=-1) @ Vc
     return out.to(q.dtype)
+
+
+def multilevel_forward(q, k, v, grid, text_length, mask_ratios, q_offsets, k_offsets, block: int = 128):
+    """AdaptiveBlockSparseAttnTrain.forward of N (N:236-267): Gilbert rearrangement with the text tokens moved to
+    the tail (N:129-152, same as C:141-161) -> sampled-max block scores (N:64-90 -> the Triton estimator, restated
+    in asa_oracle.estimator_sampled_max) -> multi-level mask (N:154-207 with the module's ratios N:13-19) ->
+    multi-level attention (K9) -> inverse rearrangement.  Returns (out, level mask, block scores)."""
+    from . import asa_oracle as O
+    rr = O.GilbertRearranger(grid[0], grid[1], grid[2], text_length)
+    qr, kr, vr = rr.rearrange(q), rr.rearrange(k), rr.rearrange(v)
+    scores = O.estimator_sampled_max(qr, kr, block, q_offsets, k_offsets)
+    mask = multilevel_mask(scores, mask_ratios)
+    out = multilevel_attention(qr.contiguous(), kr.contiguous(), vr.contiguous(), mask)
+    return rr.reversed_rearrange(out), mask, scores

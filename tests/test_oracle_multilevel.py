@@ -58,3 +58,15 @@ def test_pooled_level_equals_attention_over_pooled_keys_with_log_bias():
     v4 = v.view(1, 1, 32, 4, 64).mean(3)
     want = torch.softmax(q @ k4.transpose(-1, -2) / 8.0, -1) @ v4     # a constant bias cancels in one softmax
     assert float((got - want).abs().max()) < 2e-5
+
+
+def test_multilevel_layer_matches_reference_module(gold):
+    """N's AdaptiveBlockSparseAttnTrain.forward end to end (rearrangement, sampled-max estimator, multi-level mask,
+    multi-level attention, inverse rearrangement), its random sampling draws made explicit."""
+    q, k, v, want = (torch.from_numpy(gold[f"layer_{x}"]) for x in ("q", "k", "v", "o"))
+    w, h, d, text = (int(x) for x in gold["layer_grid_text"])
+    ratios = {int(lv): (float(a), float(b)) for lv, a, b in gold["layer_ratios"]}
+    offs = [torch.topk(torch.from_numpy(gold[f"layer_rand_{t}"]), 32, dim=3).indices[:, :, 0, :] for t in ("q", "k")]
+    got, mask, _ = M.multilevel_forward(q, k, v, (w, h, d), text, ratios, offs[0], offs[1])
+    assert set(np.unique(mask.numpy())) <= {0, 1, 2, 4, 8} and int((mask == 0).sum()) > 0
+    assert float((got - want).abs().max()) < 5e-5
