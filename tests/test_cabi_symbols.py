@@ -116,3 +116,51 @@ def test_built_library_contains_blackwell_tensor_core_and_tma_code():
         assert mnemonic in sass, mnemonic
     for legacy in ("HMMA.", "WGMMA"):
         assert legacy not in sass, legacy
+
+
+def test_argument_validation_of_the_newer_entry_points(lib):
+    """Shape / dtype / argument checks precede every CUDA call, so they can be exercised without a device: the
+    reference asserts shape equality (W:250-251) and raises ValueError for bad arguments (W:193-194)."""
+    from video_blade_b200._lib import BladeAsaConfig, BladeQkNorm, BladeTensor
+
+    def desc(shape, stride=None, dtype=0, ptr=0x1000):
+        t = BladeTensor()
+        t.ptr = ptr
+        st = stride or (shape[1] * shape[2] * shape[3], shape[2] * shape[3], shape[3], 1)
+        for i in range(4):
+            t.shape[i], t.stride[i] = shape[i], st[i]
+        t.dtype = dtype
+        return t
+    q = desc((1, 2, 256, 128))
+    k_bad = desc((1, 2, 128, 128))
+    # q/k/v shapes must agree in the layer entry points
+    rc = lib.blade_asa_prep(C.byref(q), C.byref(k_bad), C.byref(q), None, None, None, None, None, None, None, None,
+                            128, 30, None)
+    assert rc == 1 and b"shapes differ" in lib.blade_last_error()
+    # unsupported element type
+    f32 = desc((1, 2, 256, 128), dtype=2)
+    rc = lib.blade_asa_prep(C.byref(f32), C.byref(f32), C.byref(f32), None, None, None, None, None, None, None, None,
+                            128, 30, None)
+    assert rc == 2
+    # block size outside {64, 128}
+    rc = lib.blade_asa_prep(C.byref(q), C.byref(q), C.byref(q), None, None, None, None, None, None, None, None,
+                            96, 30, None)
+    assert rc == 5 and b"block_size" in lib.blade_last_error()
+    # score kernel: head dims other than 64 / 128
+    assert lib.blade_asa_scores_meanpool(0x1000, 0x1000, 0x1000, 1, 2, 16, 96, None) == 1
+    # selection: retain bounds must be positive
+    cfg = BladeAsaConfig(128, 30, 0, 4, 0.95, 0, 32, 0, 1)
+    assert lib.blade_asa_select(0x1000, 1, 1, 4, 4, C.byref(cfg), None, None, 0x1000, 0x1000, None, None, None) == 5
+    # the RMSNorm statistic needs token-major q/k
+    head_major = desc((1, 2, 256, 128))                           # [B,H,S,D] contiguous: stride_h = S*D != D
+    assert lib.blade_qk_rms_stat(C.byref(head_major), C.byref(head_major), 1e-6, 0x1000, None) == 1
+    assert b"token-major" in lib.blade_last_error()
+    # whole layer: workspace too small is reported with the size that is needed
+    out = desc((1, 2, 256, 128))
+    cfg = BladeAsaConfig(128, 30, 1, 1, 0.95, 0, 32, 0, 1)
+    need = lib.blade_asa_workspace_bytes(1, 2, 256, 128, C.byref(cfg))
+    assert need > 3 * 2 * 256 * 128 * 2
+    rc = lib.blade_asa_forward(C.byref(q), C.byref(q), C.byref(q), None, None, C.byref(cfg), None, C.byref(out),
+                               None, None, None, None, 0x10000, 1024, None)
+    assert rc == 6 and str(need).encode() in lib.blade_last_error()
+    assert C.sizeof(BladeQkNorm) == 48
