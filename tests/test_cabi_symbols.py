@@ -164,3 +164,30 @@ def test_argument_validation_of_the_newer_entry_points(lib):
                                None, None, None, None, 0x10000, 1024, None)
     assert rc == 6 and str(need).encode() in lib.blade_last_error()
     assert C.sizeof(BladeQkNorm) == 48
+
+
+def test_register_budgets_of_the_hot_kernels():
+    """Occupancy guards read from the ptxas log the build writes: the gather kernel must keep 3 CTAs per SM (<= 85
+    registers; the norm path once pushed it to 128 and cost 10-28 % of that stage), the attention kernel must fit
+    its setmaxnreg split (168 = 65536 / 384) without meaningful spills, the score kernel 3 CTAs per SM."""
+    log = os.path.join(ROOT, "video_blade_b200", "lib", "ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas log (library not built here)")
+    text = open(log).read()
+    entries = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'.*?(\d+) bytes spill stores.*?Used (\d+) registers",
+                         text, flags=re.S)
+    assert len(entries) >= 30
+    seen = {"prep": 0, "attn": 0, "score": 0}
+    for name, spill, regs in entries:
+        spill, regs = int(spill), int(regs)
+        if "prep_block_kernel" in name:
+            seen["prep"] += 1
+            assert regs <= 85, (name, regs)
+            assert spill <= 64, (name, spill)
+        elif "asa_attn_kernel" in name:
+            seen["attn"] += 1
+            assert regs <= 168 and spill <= 96, (name, regs, spill)
+        elif "score_meanpool_kernel" in name:
+            seen["score"] += 1
+            assert regs <= 85 and spill <= 32, (name, regs, spill)
+    assert seen["prep"] >= 10 and seen["attn"] == 8 and seen["score"] == 2, seen
