@@ -912,6 +912,12 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
                 int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
                 int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  // one-shot flags set by the callers for exactly this launch: consumed up front, so that an early error return
+  // cannot leak them into the next call on this thread
+  const bool sched_prezeroed = g_sched_prezeroed != 0;
+  const int sub64 = g_sub64_next;
+  g_sched_prezeroed = 0;
+  g_sub64_next = 0;
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -1001,8 +1007,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.gap = (float)sample_gap;
   p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;
   p.exact_merge = exact_merge;
-  p.sub64 = g_sub64_next;
-  g_sub64_next = 0;
+  p.sub64 = sub64;
 #ifdef BLADE_TRACE
   {
     static long long* tbuf = nullptr;  // debug build only (tools/trace_attn.py); the product never allocates
@@ -1014,8 +1019,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
 #endif
 
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
-  if (p.sched && !g_sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, sizeof(int), stream));
-  g_sched_prezeroed = 0;
+  if (p.sched && !sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, sizeof(int), stream));
   StageTimer timer(3, stream);
 #define LAUNCH_ATTN(DD, BF)                                                                                     \
   do {                                                                                                          \
