@@ -90,3 +90,35 @@ def test_pooling_and_padding_match_live_reference(ref_modules):
         x = torch.randn(1, 2, S, 32, generator=g).bfloat16()
         assert torch.equal(O.pad_to_multiple(x, 128), W.pad_to_multiple(x, 128))
         assert torch.equal(O.simple_pooling(x, gap), W.simple_pooling(x, sample_gap=gap))
+
+
+@pytest.mark.parametrize("flavor,grid,T,H,D,gap,mx", [
+    ("wan", (13, 10, 6), 0, 1, 64, 30, 0.3),        # 780 tokens: ragged last block (12 tokens)
+    ("wan", (16, 8, 4), 0, 2, 128, 7, 0.6),          # 512 tokens, exact multiple of 128, unusual gap
+    ("cog", (8, 6, 4), 10, 2, 64, 15, 0.5),          # the reference test grid (TG:76-80): 192 video + 10 text tokens
+    ("cog", (13, 10, 6), 226, 1, 64, 15, 0.2),       # CogVideoX's real text length on a small grid
+])
+def test_whole_layer_matches_live_reference_forward(ref_modules, flavor, grid, T, H, D, gap, mx):
+    """AdaptiveBlockSparseAttnTrain.forward of the LIVE reference module (external kernel and Triton estimator
+    substituted as in oracle/make_golden.py) vs oracle.asa_forward, bit for bit in bf16, with and without the
+    Gilbert rearrangement -- four more shapes than the committed golden layers."""
+    G, W, C = ref_modules
+    mod = W if flavor == "wan" else C
+    S = grid[0] * grid[1] * grid[2] + T
+    q, k, v = O.synth_qkv(1, H, S, D, seed=77 + S, structured=2.0, grid=grid, text_length=T)
+    saved = {n: getattr(mod, n) for n in ("block_sparse_attn", "attn_with_pooling", "width", "height", "depth",
+                                          "text_length", "sample_gap", "max_retain_ratio", "min_retain_ratio")}
+    try:
+        want, want_nr = G._run_reference_layer(mod, flavor, q, k, v, grid, T, gap, mx, 0.05, seed=11)
+    finally:
+        for n, val in saved.items():
+            setattr(mod, n, val)
+    cfg = O.ASAConfig(flavor=flavor, width=grid[0], height=grid[1], depth=grid[2], text_length=T, sample_gap=gap,
+                      max_retain_ratio=mx, min_retain_ratio=0.05, estimator="sampled_max")
+    for use_rr, ref in ((True, want), (False, want_nr)):
+        cfg.use_rearrange = use_rr
+        g = torch.Generator().manual_seed(11)
+        qo = O.draw_sample_offsets(1, H, cfg.block_size, cfg.num_keep, g)
+        ko = O.draw_sample_offsets(1, H, cfg.block_size, cfg.num_keep, g)
+        res = O.asa_forward(q, k, v, cfg, qo, ko)
+        assert torch.equal(res.out, ref), (flavor, grid, use_rr, float((res.out.float() - ref.float()).abs().max()))
