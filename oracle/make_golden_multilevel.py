@@ -63,6 +63,22 @@ def load_mask_fn():
     return ns["transfer_attn_to_mask"], ast.literal_eval(assign.value)
 
 
+def golden_backward(k9, out, g):
+    """K9's backward kernels (K9:695-1237, 1375-1576) under the interpreter: dq, dk, dv for a mask with every level;
+    the gradient reaches k and v through the pooled copies as well."""
+    B, H, N, D = 1, 1, 384, 64
+    q, k, v = (torch.randn(B, H, N, D, generator=g).requires_grad_(True) for _ in range(3))
+    mask = torch.tensor([[1, 2, 0], [4, 1, 8], [2, 8, 1]], dtype=torch.int32).view(1, 1, 3, 3)
+    fn = k9.sparse_attention_factory(BLOCK_M=128, BLOCK_N=128)
+    o = fn(q, k, v, mask, None)
+    do = torch.randn(B, H, N, D, generator=g)
+    o.backward(do)
+    for key, t in (("q", q), ("k", k), ("v", v), ("mask", mask), ("do", do), ("o", o), ("dq", q.grad), ("dk", k.grad),
+                   ("dv", v.grad)):
+        out[f"bwd_{key}"] = t.detach().numpy()
+    print("backward ok", float(q.grad.abs().mean()), float(k.grad.abs().mean()), float(v.grad.abs().mean()))
+
+
 def golden_layer(out):
     """The reference module N end to end on CPU: its own GilbertRearranger, random token sampling (draws recorded),
     Triton estimator and Triton multi-level kernel under the interpreter, fp32."""
@@ -144,6 +160,7 @@ def main():
         for key, t in (("q", q), ("k", k), ("v", v), ("mask", mask), ("o", o)):
             out[f"{name}_{key}"] = t.numpy()
         print(name, "ok", tuple(o.shape), float(o.abs().mean()))
+    golden_backward(k9, out, g)
     golden_layer(out)
     np.savez_compressed(os.path.join(OUT, "multilevel.npz"), **out)
     print("wrote", os.path.join(OUT, "multilevel.npz"))

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE (CPU oracle, never imported by the product path).
 
-Restatement of the reference's experimental *multi-level pooled* sparse attention, the
-forward pass only:
+Restatement of the reference's experimental *multi-level pooled* sparse attention.  The
+forward is restated here; the backward (K9:695-1237) is its plain gradient -- autograd through `multilevel_attention`
+reproduces the reference's dq / dk / dv (tests/test_oracle_multilevel.py):
   N  = cogvideox/sample_evaluate/Triton/cogvideo_newattn.py
   K9 = cogvideox/sample_evaluate/Triton/kernels/block_sparse_attn_kernel_with_backward_9_10.py
 
