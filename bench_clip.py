@@ -7,19 +7,99 @@ Ulysses N/2 (Wan has 12 heads -> N in {2,4,8}).
     python bench_clip.py [--steps 8] [--layers 30] [--reps 2]
     python -m torch.distributed.run --nproc-per-node N ... bench_clip.py --gpus N
 
-Prints one JSON line: clip seconds (max over ranks, CUDA events), and the attention share."""
+Prints one JSON line: clip seconds (max over ranks, CUDA events), and the attention share.  `run_clip` is also what
+bench.py calls to put BASELINE's second metric ("8-step clip s at 1/2/4/8 GPU") on the driver-run line."""
 from __future__ import annotations
 
 import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance=5.0, dense=False, retain=None,
+             data_plane="auto"):
+    """One process per GPU; the process group (NCCL) must exist when world > 1.  Returns the result dict on every
+    rank (value = max over ranks of the best repetition, seconds)."""
+    import torch.distributed as dist
+    from video_blade_b200.dit import WanLikeDiT, generate_new, make_velocity_fn
+    from video_blade_b200.modify_wan import set_adaptive_block_sparse_attn_wanx
+    from video_blade_b200.ulysses import UlyssesGroup
+
+    P = 1 if world == 1 else world // 2
+    group = UlyssesGroup(world, rank, P) if world > 1 else None
+    branch = 0 if world == 1 else rank // P
+    torch.manual_seed(0)
+
+    class Dense(torch.nn.Module):
+        def forward(self, q, k, v, **kw):
+            return torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    if model == "cog":
+        from video_blade_b200 import cogvideo_blocksparseattn as Cg
+        from video_blade_b200.dit import CogLikeDiT
+        from video_blade_b200.modify_cogvideo import set_block_sparse_attn_cogvideox
+        if retain is not None:
+            Cg.max_retain_ratio = Cg.min_retain_ratio = retain
+        layers = 42 if layers == 30 else layers
+        with torch.device(dev):
+            net = CogLikeDiT(layers=layers).to(torch.bfloat16).eval()
+        blocks = net.transformer_blocks
+        inner = set_block_sparse_attn_cogvideox(net)
+        net.set_sequence_parallel(group)
+        noise = torch.randn(1, 13, 16, 60, 90, generator=g).to(dev, torch.bfloat16)
+        prompt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
+        negative = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
+        wname = f"CogVideoX-5B 49x480x720, {layers} DiT blocks, {steps} steps, CFG batch 2" + \
+                (f", min=max retain {retain}" if retain is not None else "")
+    else:
+        net = WanLikeDiT(layers=layers).to(dev, torch.bfloat16).eval()
+        blocks = net.blocks
+        inner = set_adaptive_block_sparse_attn_wanx(net)
+        net.set_sequence_parallel(group, data_plane=data_plane)
+        noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
+        prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+        negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
+        wname = f"Wan2.1-T2V-1.3B 81x480x832, {layers} DiT blocks, {steps} steps, CFG batch 2"
+    inner.print_every = 0
+    if dense:
+        for blk in blocks:
+            blk.attn1.inner_attention = Dense()
+    cfg_ranks = None if world == 1 else (branch, 0, P)
+    vel = make_velocity_fn(net, prompt, negative, guidance, cfg_ranks)
+
+    with torch.no_grad():
+        generate_new(vel, noise, steps=1)                        # warm-up (cuBLAS plans, workspaces, NCCL)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            out = generate_new(vel, noise, steps=steps)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 1e3)
+    t = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    plane = getattr(net, "data_plane_in_use", "none")
+    res = {"metric": f"8-step clip seconds ({'CogVideoX-5B' if model == 'cog' else 'Wan2.1-T2V-1.3B'} shape, random init, CFG, synthetic inputs)",
+           "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
+           "config": {"workload": wname, "layers": layers, "steps": steps, "attention": "dense SDPA" if dense else "ASA",
+                      "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}", "data_plane": plane},
+           "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
+           "avg_sparsity": None if dense else inner.average_sparsity()}
+    del net, vel, out
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -32,13 +112,9 @@ def main():
     ap.add_argument("--dense", action="store_true", help="replace ASA by dense SDPA (context number)")
     ap.add_argument("--model", default="wan", choices=["wan", "cog"], help="wan = config 3, cog = config 5")
     ap.add_argument("--retain", type=float, default=None, help="cog density sweep: min = max retain ratio")
+    ap.add_argument("--data-plane", default="auto", choices=["auto", "p2p", "nccl"])
     a = ap.parse_args()
     import torch.distributed as dist
-    from video_blade_b200 import wanx_blocksparseattn as W
-    from video_blade_b200.dit import WanLikeDiT, generate_new, make_velocity_fn
-    from video_blade_b200.modify_wan import set_adaptive_block_sparse_attn_wanx
-    from video_blade_b200.ulysses import UlyssesGroup
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,78 +123,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    P = 1 if world == 1 else world // 2
-    group = UlyssesGroup(world, rank, P) if world > 1 else None
-    branch = 0 if world == 1 else rank // P
-
-    torch.manual_seed(0)
-
-    class Dense(torch.nn.Module):
-        def forward(self, q, k, v, **kw):
-            return torch.nn.functional.scaled_dot_product_attention(q, k, v)
-    g = torch.Generator(device="cpu").manual_seed(1)
-    if a.model == "cog":
-        from video_blade_b200 import cogvideo_blocksparseattn as Cg
-        from video_blade_b200.dit import CogLikeDiT
-        from video_blade_b200.modify_cogvideo import set_block_sparse_attn_cogvideox
-        if a.retain is not None:
-            Cg.max_retain_ratio = Cg.min_retain_ratio = a.retain
-        layers = 42 if a.layers == 30 else a.layers
-        with torch.device(dev):
-            model = CogLikeDiT(layers=layers).to(torch.bfloat16).eval()
-        blocks = model.transformer_blocks
-        inner = set_block_sparse_attn_cogvideox(model)
-        model.set_sequence_parallel(group)
-        noise = torch.randn(1, 13, 16, 60, 90, generator=g).to(dev, torch.bfloat16)
-        prompt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
-        negative = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
-        wname = f"CogVideoX-5B 49x480x720, {layers} DiT blocks, 8 steps, CFG batch 2" + \
-                (f", min=max retain {a.retain}" if a.retain is not None else "")
-    else:
-        layers = a.layers
-        model = WanLikeDiT(layers=a.layers).to(dev, torch.bfloat16).eval()
-        blocks = model.blocks
-        inner = set_adaptive_block_sparse_attn_wanx(model)
-        model.set_sequence_parallel(group)
-        noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
-        prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
-        negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
-        wname = f"Wan2.1-T2V-1.3B 81x480x832, {layers} DiT blocks, 8 steps, CFG batch 2"
-    inner.print_every = 0
-    if a.dense:
-        for blk in blocks:
-            blk.attn1.inner_attention = Dense()
-    cfg_ranks = None if world == 1 else (branch, 0, P)
-    vel = make_velocity_fn(model, prompt, negative, a.guidance, cfg_ranks)
-
-    def clip():
-        return generate_new(vel, noise, steps=a.steps)
-
-    with torch.no_grad():
-        generate_new(vel, noise, steps=1)                        # warm-up (cuBLAS plans, workspaces, NCCL)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        times = []
-        for _ in range(a.reps):
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            out = clip()
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1) / 1e3)
-    t = torch.tensor([min(times)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = run_clip(world, rank, dev, steps=a.steps, layers=a.layers, reps=a.reps, model=a.model, guidance=a.guidance,
+                   dense=a.dense, retain=a.retain, data_plane=a.data_plane)
     if rank == 0:
-        line = {"metric": f"8-step clip seconds ({'CogVideoX-5B' if a.model == 'cog' else 'Wan2.1-T2V-1.3B'} shape, random init, CFG, synthetic inputs)",
-                "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
-                "config": {"workload": wname,
-                           "layers": layers, "steps": a.steps, "attention": "dense SDPA" if a.dense else "ASA",
-                           "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}"},
-                "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
-                "avg_sparsity": None if a.dense else inner.average_sparsity()}
-        print(json.dumps(line))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BLADE_ABI_VERSION 1
+#define BLADE_ABI_VERSION 2
 
 enum BladeStatus {
   BLADE_OK = 0,
@@ -87,6 +87,27 @@ typedef struct BladeQkNorm {
   const void* k_bias;
 } BladeQkNorm;
 
+/* Sequence-parallel (Ulysses) data plane over NVLink peer memory (absent from the reference, whose only
+ * multi-GPU mode is whole-pipeline replicas, simple_multiprocess_sampler.py:296-339).  Outside attention rank r of a
+ * group of n_peers owns rows_per_peer consecutive TOKENS of every head ([rows_per_peer, H_total, D] token-major
+ * memory); inside it owns all tokens of H_total / n_peers heads.  Instead of an all-to-all in front of and behind the
+ * layer, the gather kernel PULLS its heads' rows of q/k/v straight out of the peers' projection outputs, and the
+ * attention epilogue PUSHES every output row into the owning peer's [rows_per_peer, H_total, D] buffer, tile by tile
+ * while the tensor cores work on the next tile.  All pointers are device addresses valid on THIS GPU (peer mappings:
+ * CUDA IPC / VMM, e.g. torch.distributed._symmetric_memory); the caller provides the cross-GPU barriers
+ * (peers' q/k/v complete before the call is enqueued; outputs visible after a barrier behind it). */
+#define BLADE_MAX_PEERS 8
+typedef struct BladePeers {
+  int32_t n_peers;         /* Ulysses degree P (1..8) */
+  int32_t my_peer;         /* my index in the group: I own heads [my_peer*H, (my_peer+1)*H) of H_total = n_peers*H */
+  int32_t rows_per_peer;   /* tokens owned by each peer: token t lives on peer t / rows_per_peer */
+  int32_t _pad;
+  const void* q[BLADE_MAX_PEERS];  /* peer p's [rows_per_peer, H_total, D] projections; NULL = q/k/v arguments are local */
+  const void* k[BLADE_MAX_PEERS];
+  const void* v[BLADE_MAX_PEERS];
+  void* out[BLADE_MAX_PEERS];      /* peer p's [rows_per_peer, H_total, D] attention output; NULL = `out` argument */
+} BladePeers;
+
 /* Knobs of the reference module (W:9-16, C:9-16 and the literals W:62,325,341). */
 typedef struct BladeAsaConfig {
   int32_t block_size;        /* 128 (W:325); 64 accepted for the selection/score stages */
@@ -105,6 +126,18 @@ typedef struct BladeAsaConfig {
   const int32_t* token_row;   /* optional device int32 [S]: token index of output row r, for the rotary table and the
                                  norm statistic, when src_row addresses a packed buffer instead of tokens (Ulysses
                                  receive layout); NULL = src_row[r] (or r) is the token index */
+  /* ---- ABI version 2 ---- */
+  const int32_t* sample_q_off; /* estimator 1: device int32 [B,H,num_keep] intra-block offsets of the sampled query tokens */
+  const int32_t* sample_k_off; /*   ... and key tokens (the reference draws them with torch.rand + topk per call, W:49-51) */
+  int32_t select_rounding;     /* prefix sums / threshold of the selection: 0 = fp32 scores (fp64-sequential sums rounded
+                                  to fp32 == torch CPU cumsum of fp32); 1 = bf16, 2 = f16: the reference's arithmetic when
+                                  Po stays in the model dtype (W:214-221: fp32-sequential sums, each prefix and
+                                  `energy_threshold * total` rounded to that dtype) */
+  int32_t _pad2;
+  unsigned long long* selected_acc; /* optional device counter: += number of selected (q-block, k-block) pairs of this
+                                  call -- the numerator of the reference's sparsity statistic (W:372) without its
+                                  per-layer host sync (W:398) */
+  const BladePeers* peers;     /* host pointer or NULL: Ulysses pull/push over peer memory (see BladePeers) */
 } BladeAsaConfig;
 
 /* ---- introspection -------------------------------------------------------------------------- */
@@ -148,6 +181,11 @@ int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, const BladeT
 /* rstd[token] = rsqrt(mean over all H*D channels of x^2 + eps) for q and k (token-major [B,S,H*D] memory):
  * rstd_out fp32 [2][B*S].  The statistic half of BladeQkNorm, for callers that shard heads after computing it. */
 int blade_qk_rms_stat(const BladeTensor* q, const BladeTensor* k, float eps, float* rstd_out, void* stream);
+/* Ulysses variant: q, k are MY token shard ([1,H_total,rows,D] views of token-major memory); the statistic is stored into
+ * every peer's full-length table rstd_peers[p] (fp32 [2][total_rows], peer-mapped device pointers) at rows
+ * [first_row, first_row + rows) -- an all-gather done by the producing kernel's own stores over NVLink. */
+int blade_qk_rms_stat_peers(const BladeTensor* q, const BladeTensor* k, float eps, float* const* rstd_peers,
+                            int32_t n_peers, int64_t total_rows, int64_t first_row, void* stream);
 
 /* ---- score estimators: fp32 [B,H,nb,nb] row-normalised block scores -------------------------- */
 int blade_asa_scores_meanpool(const float* q_mean, const float* k_mean, float* scores,
@@ -212,8 +250,11 @@ int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTe
 
 /* ---- a1: the whole layer (AdaptiveBlockSparseAttnTrain.forward) ------------------------------
  * q,k,v in the caller's token order; src_row/dst_row as above (NULL = use_rearrange False).
- * scores_in: optional fp32 [B,H,nb,nb] to bypass the estimator (parity contract);
- * scores_out / mask_out / sparsity_sum (device float, += selected fraction numerator) optional. */
+ * scores_in: optional fp32 [B,H,nb,nb] to bypass the estimator (parity contract); scores_out / mask_out optional.
+ * cfg->estimator 0 = block-mean-pool scores, 1 = the reference's sampled-max estimator (needs cfg->sample_*_off).
+ * cfg->block_size 64 (BASELINE config 1): scores / mask_out / cnt_out are 64-granular ([.., nb64, nb64] / [.., nb64]);
+ * idx_out, if given, receives the quadrant-flagged 128-tile lists [B,H,ceil(nb64/2),ceil(nb64/2)].
+ * The running sparsity numerator goes to cfg->selected_acc (device counter, no host sync). */
 int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
                       const int32_t* src_row, const int32_t* dst_row,
                       const BladeAsaConfig* cfg, const float* scores_in,
@@ -224,7 +265,8 @@ int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTen
 /* ---- measurement hook ------------------------------------------------------------------------
  * When set, the library records the given cudaEvent_t pair (passed as void*) on the caller's stream
  * immediately before / after the launches of one stage, so a harness can time a kernel INSIDE a whole-layer
- * call.  stage: 0 = prep (+pool), 1 = scores, 2 = select, 3 = attention.  NULL,NULL clears the slot. */
+ * call.  stage: 0 = prep (gather + block means), 1 = scores, 2 = select, 3 = attention, 4 = gap pooling (runs on the
+ * library's side stream, concurrently with 1 and 2).  NULL,NULL clears the slot.  Per calling thread. */
 int blade_profile_events(int32_t stage, void* start_event, void* stop_event);
 
 /* ---- bring-up probes (tests only): single-tile tcgen05 GEMMs dumped from TMEM --------------- */

@@ -37,9 +37,9 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from video_blade_b200._lib import BladeAsaConfig, BladeTensor
-    assert lib.blade_abi_version() == 1
+    assert lib.blade_abi_version() == 2
     assert C.sizeof(BladeTensor) == 8 + 32 + 32 + 8
-    assert C.sizeof(BladeAsaConfig) == 16 * 4
+    assert C.sizeof(BladeAsaConfig) == 16 * 4 + 40          # ABI 2: sample offsets, select_rounding, selected_acc, peers
 
 
 def test_gilbert_tables_match_reference_hashes(lib):

@@ -542,3 +542,116 @@ def test_many_items_per_cta_nonuniform_rows_vs_torch_fp32():
             want = torch.softmax(s, -1) @ v[b, h].float()
             _close(out[b, h], want.to(torch.bfloat16))
             _close(lse[b, h], torch.logsumexp(s, -1), 1e-5, 1e-4)
+
+
+# ------------------------------------------------------------------ the benchmarked sizes (BASELINE configs 2 and 4)
+def _full_size_layer(flavor, H, seed, structured):
+    """Whole layer -- gather, estimator, selection, sparse branch, pooled branch, bf16 merge, inverse permute -- at the
+    size bench.py times, against `O.asa_forward(fast=True)` (the oracle evaluated over the selected blocks only) fed
+    the kernel's own fp32 scores: mask bit-exact, merged output within the north-star tolerance.  Also reports how
+    many rows differ noticeably (a flipped bf16 rounding of an lse moves the merge weight of the whole row)."""
+    from video_blade_b200.asa import AsaEngine, AsaKnobs
+    kn = AsaKnobs.cog() if flavor == "cog" else AsaKnobs.wan()
+    cfg = O.ASAConfig.cog() if flavor == "cog" else O.ASAConfig.wan()
+    D = 64 if flavor == "cog" else 128
+    grid = (kn.width, kn.height, kn.depth)
+    S = grid[0] * grid[1] * grid[2] + kn.text_length
+    q, k, v = O.synth_qkv(1, H, S, D, seed=seed, structured=structured, grid=grid, text_length=kn.text_length)
+    # strided views of token-major memory, as the processors hand them over (MW:104-106 / MC:47-52)
+    qc, kc, vc = (x.transpose(1, 2).contiguous().cuda().transpose(1, 2) for x in (q, k, v))
+    eng = AsaEngine(kn)
+    out, dbg = eng.forward(qc, kc, vc, return_debug=True)
+    torch.cuda.synchronize()
+    nb = -(-S // 128)
+    assert dbg["scores"].shape == (1, H, nb, nb)
+    rr = O.GilbertRearranger(*grid, text_length=kn.text_length)
+    want_sc = O.estimator_meanpool(rr.rearrange(q), rr.rearrange(k), 128)
+    _close(dbg["scores"], want_sc, 1e-4, 1e-5)
+    ref = O.asa_forward(q, k, v, cfg, scores=dbg["scores"].cpu(), fast=True, rearranger=rr)
+    assert torch.equal(dbg["mask"].cpu(), ref.mask)                        # bit-exact selection (incl. forced rows/cols)
+    widx, wcnt = O.mask_to_index_list(ref.mask)
+    assert torch.equal(dbg["idx"].cpu(), widx) and torch.equal(dbg["cnt"].cpu(), wcnt)
+    r, m = _close(out, ref.out)
+    row_err = (out.float().cpu() - ref.out.float()).abs().amax(-1)         # [1,H,S]
+    flip = float((row_err > 4e-3).float().mean())
+    lo, hi = kn.retain_bounds(nb)
+    cnt = dbg["cnt"].cpu()
+    print(f"[full-size {flavor}] S={S} H={H} nb={nb} retained/row min={int(cnt.min())} mean={float(cnt.float().mean()):.1f} "
+          f"max={int(cnt.max())} (clamp [{lo},{hi}]) rel_l2={r:.2e} max_abs={m:.2e} rows>4e-3: {flip:.2e}")
+    return cnt, lo, hi
+
+
+@pytest.mark.parametrize("structured", [0.0, 2.0])
+def test_full_size_wan_layer_vs_oracle(structured):
+    """BASELINE config 2: Wan 52x30x21 = 32 760 tokens, d = 128, tail block of 120 rows, 1 092 pooled keys."""
+    cnt, lo, hi = _full_size_layer("wan", H=2, seed=41, structured=structured)
+    assert int(cnt.min()) >= lo and int(cnt.max()) <= hi
+
+
+@pytest.mark.parametrize("structured", [0.0, 2.0])
+def test_full_size_cog_layer_vs_oracle(structured):
+    """BASELINE config 4: CogVideoX 45x30x13 + 226 text = 17 776 tokens, d = 64, nb = 139, tail block of 112 rows,
+    text tokens moved to the tail, last two block rows/cols forced dense (C:247-248), 1 186 pooled keys."""
+    cnt, lo, hi = _full_size_layer("cog", H=3, seed=43, structured=structured)
+    nb = cnt.shape[-1]
+    assert torch.all(cnt[..., -2:] == nb)                                  # forced dense rows
+    assert int(cnt[..., :-2].min()) >= min(lo, 2) and int(cnt[..., :-2].max()) <= hi + 2   # + the two forced columns
+
+
+# ------------------------------------------------------------------ selection on half-precision scores (ADVICE r1)
+@pytest.mark.parametrize("dt,mode", [(torch.bfloat16, "bf16"), (torch.float16, "f16")])
+def test_select_half_precision_rounding_matches_torch(dt, mode):
+    """The reference keeps Po in the model dtype: sort / cumsum / `0.95 * total` / compare all run on bf16 tensors
+    (W:214-221).  select_rounding reproduces torch's arithmetic for that (fp32-sequential prefix sums, each prefix and
+    the threshold rounded to the dtype): bit-exact against the oracle evaluated ON the half-precision tensor."""
+    g = torch.Generator().manual_seed(11)
+    for nb, flavor in ((256, "wan"), (139, "cog"), (61, "wan")):
+        sc = torch.softmax(torch.randn(1, 4, nb, nb, generator=g) * 2.5, -1).to(dt)
+        lo, hi = O.retain_bounds(nb, 0.05, 0.17 if flavor == "wan" else 0.1, flavor)
+        force = 2 if flavor == "cog" else 0
+        want, _ = O.select_blocks_energy(sc, lo, hi, 0.95, force_last=force)          # torch ops on the bf16 tensor
+        want32, _ = O.select_blocks_energy(sc.float(), lo, hi, 0.95, force_last=force)
+        eng = _engine(flavor=flavor, select_rounding=mode)
+        idx, cnt, mask = eng.select(sc.float().cuda(), lo=lo, hi=hi, force_last=force)
+        assert torch.equal(mask.cpu(), want), (nb, flavor, int((mask.cpu() != want).sum()))
+        eng32 = _engine(flavor=flavor)
+        _, _, mask32 = eng32.select(sc.float().cuda(), lo=lo, hi=hi, force_last=force)
+        assert torch.equal(mask32.cpu(), want32)
+
+
+def test_selected_counter_accumulates_on_device():
+    eng = _engine(width=26, height=15, depth=4, max_retain_ratio=0.4)
+    q, k, v = O.synth_qkv(1, 2, 1560, 128, seed=2, structured=2.0, grid=(26, 15, 4))
+    acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    tot = 0
+    for _ in range(3):
+        _, cnt = eng.forward(q.cuda(), k.cuda(), v.cuda(), selected_acc=acc)
+        tot += int(cnt.sum())
+    assert int(acc.item()) == tot and tot > 0
+
+
+def test_sampled_max_one_call_with_fused_rope_and_offsets():
+    """estimator = sampled_max through blade_asa_forward (one C-ABI call): scores equal the stand-alone estimator on
+    the gathered + rotated q/k, mask bit-exact from them, output within tolerance of the oracle."""
+    grid = (26, 15, 4)
+    S, H, D = 1560, 2, 128
+    q, k, v = O.synth_qkv(1, H, S, D, seed=29, structured=2.0, grid=grid)
+    g = torch.Generator().manual_seed(2)
+    ang = torch.rand(1, 1, S, D // 2, generator=g, dtype=torch.float64) * 6.28
+    freqs = torch.polar(torch.ones_like(ang), ang)
+    table = torch.stack([freqs.real, freqs.imag], -1).reshape(S, D // 2, 2).float().contiguous().cuda()
+    eng = _engine(width=grid[0], height=grid[1], depth=grid[2], estimator="sampled_max", max_retain_ratio=0.3)
+    qo = O.draw_sample_offsets(1, H, 128, 32, g)
+    ko = O.draw_sample_offsets(1, H, 128, 32, g)
+    out, dbg = eng.forward(q.cuda(), k.cuda(), v.cuda(), return_debug=True, sample_offsets=(qo.cuda(), ko.cuda()),
+                           rope=(table, 0))
+    (qr, kr, vr), _, _ = eng.prep(q.cuda(), k.cuda(), v.cuda(), rearrange=True, want_means=False, want_pool=False,
+                                  rope=(table, 0))
+    sc = eng.scores_sampled(qr, kr, qo.cuda(), ko.cuda())
+    assert torch.equal(sc, dbg["scores"])
+    cfg = O.ASAConfig.wan(width=grid[0], height=grid[1], depth=grid[2], estimator="sampled_max", max_retain_ratio=0.3,
+                          use_rearrange=False)
+    ref = O.asa_forward(qr.cpu(), kr.cpu(), vr.cpu(), cfg, scores=dbg["scores"].cpu())
+    assert torch.equal(dbg["mask"].cpu(), ref.mask)
+    rr = O.GilbertRearranger(*grid)
+    _close(out, rr.reversed_rearrange(ref.out))

@@ -10,6 +10,14 @@ import torch.nn as nn
 from oracle import asa_oracle as O
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The CUDA path is forward-only and refuses inputs that require grad while autograd records
+    (tests/test_host_logic.py::test_forward_only_guard): run the processors the way inference does."""
+    with torch.no_grad():
+        yield
+
+
 class _Block(nn.Module):
     def __init__(self, dim, heads, qk_norm):
         super().__init__()
@@ -204,3 +212,38 @@ def test_norm_fusion_is_only_claimed_for_known_modules():
     Fake.__name__ = "RMSNorm"
     Fake.__module__ = "diffusers.models.normalization"
     assert _rms_kind(Fake()) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("estimator", ["sampled_max", "meanpool"])
+def test_wan_processor_installer_defaults_with_each_estimator(estimator):
+    """The installer's default processor (fused rope + fused RMSNorm) must work with the reference's estimator too:
+    the one-call layer applies norm and rotation in the gather kernel for every estimator (the staged
+    sampled-max path used to raise on the fused norm)."""
+    from video_blade_b200 import modify_wan as MW, wanx_blocksparseattn as W
+    grid = (26, 15, 4)
+    S, H, D = grid[0] * grid[1] * grid[2], 2, 128
+    W.width, W.height, W.depth, W.max_retain_ratio, W.estimator = *grid, 0.4, estimator
+    try:
+        torch.manual_seed(0)
+        model = types.SimpleNamespace(blocks=nn.ModuleList([_Block(H * D, H, "rms_norm_across_heads")]))
+        model.blocks.to("cuda", torch.bfloat16)
+        inner = MW.set_adaptive_block_sparse_attn_wanx(model)
+        inner.print_every = 0
+        attn = model.blocks[0].attn1
+        x = torch.randn(1, S, H * D, device="cuda", dtype=torch.bfloat16)
+        ang = torch.rand(1, 1, S, D // 2, device="cuda") * 6.28
+        freqs = torch.polar(torch.ones_like(ang), ang)
+        torch.manual_seed(5)                                              # the module draws the sample offsets (W:49-51)
+        out = attn(x, rotary_emb=freqs)
+        attn.set_processor(MW.WanAttnProcessor2_0(fuse_rope=False, fuse_norm=False))
+        torch.manual_seed(5)
+        out_t = attn(x, rotary_emb=freqs)
+        assert torch.isfinite(out.float()).all()
+        dd = out.float() - out_t.float()
+        # fused vs torch norm/rope differ by bf16 roundings of q/k; with the sampled estimator that can move a block in
+        # or out of a row's selection, so the bound is the loose one
+        assert float(dd.norm() / out_t.float().norm()) <= (3e-2 if estimator == "sampled_max" else 1e-2)
+        assert 0.0 < inner.average_sparsity() < 1.0                       # device counter fed by the selection kernel
+    finally:
+        W.width, W.height, W.depth, W.max_retain_ratio, W.estimator = 52, 30, 21, 0.17, "meanpool"

@@ -66,6 +66,12 @@ def _worker_fused(rank, world, degree, port, S, H, D):
         sl = slice(pr * (S // degree), (pr + 1) * (S // degree))
         qv, kv, vv, vrow, keep = ug.scatter_heads_fused(*(x[:, sl].contiguous() for x in full))
         Hl = H // degree
+        if degree == 1:
+            # degree 1 must not touch the WORLD group (two CFG groups of one rank each): identity views of my sequence
+            assert torch.equal(vrow, torch.arange(S, dtype=torch.int32))
+            for view, ref in zip((qv, kv, vv), full):
+                assert view.shape == (1, H, S, D) and torch.equal(view, ref.transpose(1, 2))
+            return
         flat = keep.reshape(-1)
         for view, ref in zip((qv, kv, vv), full):
             assert view.shape == (1, Hl, S, D) and view.stride(2) == Hl * D and view.stride(1) == D
@@ -80,7 +86,7 @@ def _worker_fused(rank, world, degree, port, S, H, D):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,degree", [(2, 2), (4, 4)])
+@pytest.mark.parametrize("world,degree", [(2, 2), (4, 4), (2, 1), (4, 2)])
 def test_ulysses_fused_scatter_layout_gloo(world, degree):
     port = _free_port()
     mp.spawn(_worker_fused, args=(world, degree, port, 24, 12, 8), nprocs=world, join=True)

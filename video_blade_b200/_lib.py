@@ -25,12 +25,23 @@ class BladeQkNorm(C.Structure):
                 ("rstd", C.c_void_p), ("q_bias", C.c_void_p), ("k_bias", C.c_void_p)]
 
 
+MAX_PEERS = 8
+
+
+class BladePeers(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("my_peer", C.c_int32), ("rows_per_peer", C.c_int32), ("_pad", C.c_int32),
+                ("q", C.c_void_p * MAX_PEERS), ("k", C.c_void_p * MAX_PEERS), ("v", C.c_void_p * MAX_PEERS),
+                ("out", C.c_void_p * MAX_PEERS)]
+
+
 class BladeAsaConfig(C.Structure):
     _fields_ = [("block_size", C.c_int32), ("sample_gap", C.c_int32), ("min_retain", C.c_int32),
                 ("max_retain", C.c_int32), ("energy_threshold", C.c_float), ("force_last", C.c_int32),
                 ("num_keep", C.c_int32), ("estimator", C.c_int32), ("exact_merge", C.c_int32),
                 ("rope_first_row", C.c_int32), ("rope_cos_sin", C.c_void_p), ("qk_norm", C.POINTER(BladeQkNorm)),
-                ("token_row", C.c_void_p)]
+                ("token_row", C.c_void_p),
+                ("sample_q_off", C.c_void_p), ("sample_k_off", C.c_void_p), ("select_rounding", C.c_int32),
+                ("_pad2", C.c_int32), ("selected_acc", C.c_void_p), ("peers", C.POINTER(BladePeers))]
 
 
 # every symbol include/blade_asa.h declares (tests/test_cabi_symbols.py checks the list against the header)
@@ -40,7 +51,7 @@ SYMBOLS = [
     "blade_mask_to_index", "blade_block_sparse_attn_fwd", "blade_asa_attn_fwd", "blade_asa_forward",
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
     "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
-    "blade_attn_workspace_bytes", "blade_qk_rms_stat",
+    "blade_attn_workspace_bytes", "blade_qk_rms_stat", "blade_qk_rms_stat_peers",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -65,6 +76,7 @@ def load() -> C.CDLL:
     lib.blade_asa_workspace_bytes.argtypes = [i64, i64, i64, i64, CFG]
     lib.blade_asa_workspace_bytes.restype = C.c_size_t
     lib.blade_qk_rms_stat.argtypes = [T, T, f32, vp, vp]
+    lib.blade_qk_rms_stat_peers.argtypes = [T, T, f32, C.POINTER(vp), i32, i64, i64, vp]
     lib.blade_attn_workspace_bytes.argtypes = [i64]
     lib.blade_attn_workspace_bytes.restype = C.c_size_t
     lib.blade_asa_prep.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]

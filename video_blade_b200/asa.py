@@ -9,6 +9,7 @@ streams only.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -37,6 +38,7 @@ class AsaKnobs:
     energy_threshold: float = 0.95
     estimator: str = "meanpool"     # "meanpool" (north-star kernel (a)); "sampled_max" = reference P (next)
     exact_merge: bool = True        # reproduce the bf16 op chain of W:351-370
+    select_rounding: str = "fp32"   # "bf16"/"f16": prefix sums and threshold rounded like torch on a half-precision Po
 
     @staticmethod
     def wan(**kw) -> "AsaKnobs":
@@ -71,6 +73,7 @@ class AsaKnobs:
         cfg.num_keep = self.num_keep
         cfg.estimator = 0 if self.estimator == "meanpool" else 1
         cfg.exact_merge = 1 if self.exact_merge else 0
+        cfg.select_rounding = {"fp32": 0, "bf16": 1, "f16": 2}[self.select_rounding]
         return cfg
 
 
@@ -94,6 +97,38 @@ def token_order(knobs: AsaKnobs) -> np.ndarray:
     return c2r.astype(np.int32)
 
 
+def _on_tensor_device(fn):
+    """Every C-ABI launch goes to the CURRENT device's stream (`_lib.current_stream`) and the library reads
+    cudaGetDevice for its per-device state: run the entry point with the tensors' device current, and refuse
+    tensors that live on different devices (a foreign pointer on the wrong stream is an illegal access at best)."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        dev = None
+        for a in list(args) + list(kw.values()):
+            for t in (a if isinstance(a, (tuple, list)) else (a,)):
+                if torch.is_tensor(t) and t.is_cuda:
+                    if dev is None:
+                        dev = t.device
+                    elif t.device != dev:
+                        raise RuntimeError(f"video_blade_b200: tensors on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return wrapper
+
+
+def require_no_grad(*tensors):
+    """The C ABI is forward-only (no backward entry point): an output written through raw pointers has no grad_fn, so
+    a training caller (the reference module sits inside train_*_tdm.py) would silently get zero gradient through the
+    attention.  Fail loudly instead."""
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            "video_blade_b200 ASA is forward-only: q/k/v (or the fused norm weights) require grad but the CUDA path has "
+            "no backward kernel.  Run under torch.no_grad() / detach the inputs (inference), or use the reference "
+            "module for training.")
+
+
 class AsaEngine:
     """Owns device-side tables + workspace for one (device, knobs) and drives the kernels."""
 
@@ -102,6 +137,7 @@ class AsaEngine:
         self.lib = _lib.load()
         self._src_row = {}      # device -> int32 tensor
         self._ws = {}           # (device, bytes) -> uint8 tensor
+        self._sel_acc = {}      # device -> int64 [1] running count of selected block pairs
         self._order_np: Optional[np.ndarray] = None
 
     # ---- tables / workspace --------------------------------------------------------------
@@ -135,6 +171,7 @@ class AsaEngine:
                 raise RuntimeError("video_blade_b200 runs on CUDA tensors only (no CPU fallback)")
 
     # ---- stage entry points (same roles as the reference helpers) ------------------------
+    @_on_tensor_device
     def select(self, scores: torch.Tensor, lo=None, hi=None, force_last=None, thr=None,
                want_mask=True):
         """transfer_attn_to_mask(mode='energy') on fp32 scores [B,H,nq,nk] -> (idx, cnt, mask)."""
@@ -158,6 +195,7 @@ class AsaEngine:
                                         idx.data_ptr(), cnt.data_ptr(), ptr(mask), None, current_stream()))
         return idx, cnt, (mask.bool() if want_mask else None)
 
+    @_on_tensor_device
     def mask_to_index(self, mask: torch.Tensor):
         self._require_cuda(mask)
         m = mask.to(torch.uint8).contiguous()
@@ -168,6 +206,7 @@ class AsaEngine:
                                            current_stream()))
         return idx, cnt
 
+    @_on_tensor_device
     def prep(self, q, k, v, rearrange: bool, want_means=True, want_pool=True, rope=None):
         """Gather into Gilbert order (optional) + block means + gap-pooled K/V.  rope = (table fp32 [rows,D/2,2],
         first_row): rotary embedding of q and k fused into the gather (needs the output copies)."""
@@ -197,6 +236,7 @@ class AsaEngine:
                                            kn.block_size, gap, ptr(table), int(first), current_stream()))
         return (q_r, k_r, v_r), (qm, km), (kp, vp)
 
+    @_on_tensor_device
     def scores_meanpool(self, qm: torch.Tensor, km: torch.Tensor) -> torch.Tensor:
         B, H, nb, D = qm.shape
         sc = torch.empty(B, H, nb, nb, dtype=torch.float32, device=qm.device)
@@ -211,6 +251,7 @@ class AsaEngine:
         rand = torch.rand(B, H, 1, kn.block_size, device=device, generator=generator)
         return torch.topk(rand, kn.num_keep, dim=3).indices[:, :, 0].to(torch.int32).contiguous()
 
+    @_on_tensor_device
     def scores_sampled(self, q, k, q_off, k_off):
         """efficient_attn_with_pooling (W:62-87): fp32 [B,H,nb,nb] holding the q.dtype-rounded Po."""
         self._require_cuda(q, k, q_off, k_off)
@@ -230,43 +271,10 @@ class AsaEngine:
                                                 _lib._dtype_code(q), current_stream()))
         return sc
 
-    def _forward_staged(self, q, k, v, q_off, k_off, return_debug, scores=None, rope=None):
-        """The layer as separate C-ABI calls (prep, score, select, attention): used for estimator ==
-        "sampled_max" and for block_size 64 (blade_asa_forward covers the default block-128 mean-pool path)."""
-        B, H, S, D = q.shape
-        kn = self.knobs
-        rearr = kn.use_rearrange
-        sampled = kn.estimator == "sampled_max" and scores is None
-        (qr, kr, vr), (qm, km), (kp, vp) = self.prep(q, k, v, rearrange=rearr, want_means=not sampled and scores is None,
-                                                     rope=rope)
-        if qr is None:
-            qr, kr, vr = q, k, v
-        if scores is not None:
-            sc = scores
-        elif sampled:
-            if q_off is None:
-                q_off = self.draw_offsets(B, H, q.device)
-                k_off = self.draw_offsets(B, H, q.device)
-            sc = self.scores_sampled(qr, kr, q_off, k_off)
-        else:
-            sc = self.scores_meanpool(qm, km)
-        src = self.src_row(q.device, S)
-        if kn.block_size == 64:
-            idx64, cnt64, mask = self.select(sc, want_mask=True)
-            idx, cnt = self.mask64_to_index(mask)
-            out = self.asa_attn(qr, kr, vr, idx, cnt, kp, vp, dst_row=src, sub64=True)
-            if return_debug:
-                return out, dict(scores=sc, mask=mask, idx=idx, cnt=cnt64)
-            return out, cnt64
-        idx, cnt, mask = self.select(sc, want_mask=return_debug)
-        out = self.asa_attn(qr, kr, vr, idx, cnt, kp, vp, dst_row=src)
-        if return_debug:
-            return out, dict(scores=sc, mask=mask, idx=idx, cnt=cnt)
-        return out, cnt
-
     def _park(self, device, D):
         return self.workspace(device, int(self.lib.blade_attn_workspace_bytes(D)))
 
+    @_on_tensor_device
     def block_sparse_attn(self, q, k, v, idx, cnt, out=None, dst_row=None, want_lse=True, sub64=False):
         """block_sparse_attn(q,k,v,block_mask) (W:278-309) on an index list; returns (out, lse fp32 [B,H,S])."""
         self._require_cuda(q, k, v, idx, cnt)
@@ -283,6 +291,7 @@ class AsaEngine:
             current_stream()))
         return out, lse
 
+    @_on_tensor_device
     def mask64_to_index(self, mask64: torch.Tensor):
         """block_size 64: bool mask [B,H,nq64,nk64] -> quadrant-flagged list over 128x128 tiles."""
         self._require_cuda(mask64)
@@ -295,6 +304,7 @@ class AsaEngine:
                                              current_stream()))
         return idx, cnt
 
+    @_on_tensor_device
     def asa_attn(self, q, k, v, idx, cnt, k_pool, v_pool, out=None, dst_row=None, exact_merge=None, sub64=False):
         """Sparse branch + pooled branch + merge (W:343-370) in one launch."""
         self._require_cuda(q, k, v, idx, cnt, k_pool, v_pool)
@@ -311,6 +321,7 @@ class AsaEngine:
             current_stream()))
         return out
 
+    @_on_tensor_device
     def qk_rms_stat(self, q, k, eps: float):
         """rstd of the processor's RMSNorm over all heads' channels (MW:99-102) for q and k: fp32 [2, B*S].
         q, k: [B,H,S,D] views of token-major [B,S,H*D] memory."""
@@ -322,34 +333,55 @@ class AsaEngine:
         return out
 
     # ---- the whole layer ------------------------------------------------------------------
+    def selected_counter(self, device) -> torch.Tensor:
+        """Device counter (uint64 as int64 [1]) that every layer call adds its number of selected (q-block, k-block)
+        pairs to -- the numerator of the reference's sparsity statistic (W:372) without the per-layer `.item()` sync
+        (W:398) and without extra torch launches."""
+        key = str(device)
+        if key not in self._sel_acc:
+            self._sel_acc[key] = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._sel_acc[key]
+
+    @_on_tensor_device
     def forward(self, q, k, v, scores: Optional[torch.Tensor] = None, return_debug: bool = False,
-                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None, qk_norm=None):
+                virtual_rows: Optional[torch.Tensor] = None, sample_offsets=None, rope=None, qk_norm=None,
+                peers=None, out: Optional[torch.Tensor] = None, selected_acc: Optional[torch.Tensor] = None):
         """AdaptiveBlockSparseAttnTrain.forward (W:383-408 / C:405-427): q,k,v [B,H,S,D] in the caller's
         token order (strided views allowed) -> out [B,H,S,D] (a transposed view of [B,S,H,D] memory, so the
-        processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous.
+        processor's `.transpose(1,2).flatten(2,3)` is free).  One C-ABI call, asynchronous, for every knob
+        combination (estimator mean-pool / sampled-max, block 128 / 64).
         `qk_norm` (optional): (kind, q_weight [H*D], k_weight [H*D], eps) -- the processor's RMSNorm over all heads'
-        channels (MW:99-102), applied to q and k inside the gather kernel (include/blade_asa.h: BladeQkNorm)."""
+        channels (MW:99-102), applied to q and k inside the gather kernel (include/blade_asa.h: BladeQkNorm).
+        `sample_offsets` (sampled_max): (q_off, k_off) int32 [B,H,num_keep]; drawn like W:49-51 when omitted.
+        `peers` (optional, _lib.BladePeers): Ulysses pull/push over NVLink peer memory -- q/k/v describe the layout
+        only, rows are read from the peers' buffers and the output is written into the peers' buffers (returns
+        out = None; the caller owns the barriers)."""
         self._require_cuda(q, k, v, scores)
         B, H, S, D = q.shape
         kn = self.knobs
         dev = q.device
-        if (kn.estimator == "sampled_max" and scores is None) or kn.block_size == 64:
-            if virtual_rows is not None:
-                raise ValueError("staged path (sampled_max / block 64): the packed Ulysses receive layout is not wired yet")
-            qo, ko = sample_offsets if sample_offsets is not None else (None, None)
-            if qk_norm is not None:
-                raise ValueError("staged path (sampled_max / block 64): fused q/k norm is not wired")
-            return self._forward_staged(q, k, v, qo, ko, return_debug, scores=scores, rope=rope)
         nb = -(-S // kn.block_size)
         cfg = kn.c_config(nb)
-        norm_keep = None
+        keep = []                                                   # tensors the C structs point into
+        if kn.estimator == "sampled_max" and scores is None:
+            assert kn.num_keep == 32, "the estimator kernel is built for num_keep = 32 (W:62)"
+            qo, ko = sample_offsets if sample_offsets is not None else (None, None)
+            if qo is None:
+                qo, ko = self.draw_offsets(B, H, dev), self.draw_offsets(B, H, dev)
+            qo, ko = qo.to(torch.int32).contiguous(), ko.to(torch.int32).contiguous()
+            assert tuple(qo.shape) == (B, H, kn.num_keep) and tuple(ko.shape) == (B, H, kn.num_keep)
+            keep += [qo, ko]
+            cfg.sample_q_off, cfg.sample_k_off = qo.data_ptr(), ko.data_ptr()
+        sel = selected_acc if selected_acc is not None else self.selected_counter(dev)
+        assert sel.dtype == torch.int64 and sel.device == dev
+        cfg.selected_acc = sel.data_ptr()
         if qk_norm is not None:
             kind, wq, wk, eps = qk_norm[:4]
             rstd = qk_norm[4] if len(qk_norm) > 4 else None      # statistic computed elsewhere, fp32 [2, B*S] by token
             bq, bk = (qk_norm[5], qk_norm[6]) if len(qk_norm) > 6 else (None, None)   # kind 3: LayerNorm biases
             per_head = int(kind) == 3
-            if virtual_rows is not None and rstd is None and not per_head:
-                raise ValueError("fused q/k norm on the packed Ulysses layout needs the statistic (qk_rms_stat)")
+            if (virtual_rows is not None or peers is not None) and rstd is None and not per_head:
+                raise ValueError("fused q/k norm on the sharded Ulysses layout needs the statistic (qk_rms_stat)")
             n_w = D if per_head else H * D
             assert wq.dtype == q.dtype and wk.dtype == q.dtype and wq.numel() == n_w and wk.numel() == n_w
             wq, wk = wq.contiguous(), wk.contiguous()
@@ -358,9 +390,9 @@ class AsaEngine:
             if bq is not None:
                 assert bq.dtype == q.dtype and bk.dtype == q.dtype and bq.numel() == D and bk.numel() == D
                 bq, bk = bq.contiguous(), bk.contiguous()
-            norm_keep = (BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr(), ptr(rstd), ptr(bq), ptr(bk)),
-                         wq, wk, bq, bk)
-            cfg.qk_norm = C.pointer(norm_keep[0])
+            norm = BladeQkNorm(int(kind), float(eps), wq.data_ptr(), wk.data_ptr(), ptr(rstd), ptr(bq), ptr(bk))
+            keep += [norm, wq, wk, bq, bk, rstd]
+            cfg.qk_norm = C.pointer(norm)
         if rope is not None:
             table, first = rope
             assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[-2:] == (D // 2, 2)
@@ -368,13 +400,22 @@ class AsaEngine:
             cfg.rope_first_row = int(first)
         src = self.src_row(dev, S)
         dst = src
+        if peers is not None:
+            assert virtual_rows is None and B == 1
+            cfg.peers = C.pointer(peers)
+            keep.append(peers)
         if virtual_rows is not None:
             # q/k/v rows live at `virtual_rows[s]` of a packed buffer (Ulysses receive layout): compose the gather
             # table with it; the output permutation is unchanged.
-            key = ("v", str(dev), S, virtual_rows.data_ptr())
-            if key not in self._src_row:
-                self._src_row[key] = (virtual_rows[src.long()] if src is not None else virtual_rows).contiguous()
-            src = self._src_row[key]
+            # cached per table OBJECT (a held reference + its version counter): a bare data_ptr key would hand a
+            # stale composition to a new tensor that reuses a freed address
+            key = ("v", str(dev), S)
+            ent = self._src_row.get(key)
+            if ent is None or ent[0] is not virtual_rows or ent[1] != virtual_rows._version:
+                comp = (virtual_rows[src.long()] if src is not None else virtual_rows).contiguous()
+                ent = (virtual_rows, virtual_rows._version, comp)
+                self._src_row[key] = ent
+            src = ent[2]
             if rope is not None or qk_norm is not None:
                 # the rotary table and the norm statistic are indexed by token, not by packed-buffer row
                 tok = dst
@@ -386,20 +427,26 @@ class AsaEngine:
                 cfg.token_row = tok.data_ptr()
         nbytes = self.lib.blade_asa_workspace_bytes(B, H, S, D, C.byref(cfg))
         ws = self.workspace(dev, nbytes)
-        out = torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)
+        if peers is not None:
+            out_t = q                                              # layout descriptor only: rows go to peers.out[*]
+        else:
+            out_t = out if out is not None else torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)
         cnt = torch.empty(B, H, nb, dtype=torch.int32, device=dev)
         sc_out = mask = idx = None
         if return_debug:
+            n_idx = -(-nb // 2) if kn.block_size == 64 else nb     # block 64: lists over the 128x128 tensor-core tiles
             sc_out = torch.empty(B, H, nb, nb, dtype=torch.float32, device=dev)
             mask = torch.empty(B, H, nb, nb, dtype=torch.uint8, device=dev)
-            idx = torch.empty(B, H, nb, nb, dtype=torch.int32, device=dev)
+            idx = torch.empty(B, H, n_idx, n_idx, dtype=torch.int32, device=dev)
         if scores is not None:
             scores = scores.contiguous()
             assert scores.dtype == torch.float32 and tuple(scores.shape) == (B, H, nb, nb)
         check(self.lib.blade_asa_forward(
             C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), ptr(src), ptr(dst),
-            C.byref(cfg), ptr(scores), C.byref(tensor_desc(out)), ptr(sc_out), ptr(mask), ptr(idx), cnt.data_ptr(),
+            C.byref(cfg), ptr(scores), C.byref(tensor_desc(out_t)), ptr(sc_out), ptr(mask), ptr(idx), cnt.data_ptr(),
             ws.data_ptr(), ws.numel(), current_stream()))
+        del keep
+        res = None if peers is not None else out_t
         if return_debug:
-            return out, dict(scores=sc_out, mask=mask.bool(), idx=idx, cnt=cnt)
-        return out, cnt
+            return res, dict(scores=sc_out, mask=mask.bool(), idx=idx, cnt=cnt)
+        return res, cnt

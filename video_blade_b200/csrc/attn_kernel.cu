@@ -118,6 +118,10 @@ struct AttnParams {
   float gap;               // float(sample_gap) for the non-emulated merge
   int exact_merge;
   int sub64;  // 1: list entries carry a 4-bit quadrant mask in bits 28..31 (64x64 mask granularity on 128x128 tiles)
+  // Ulysses push (BladePeers): output row `dst` (a token index) goes to peer dst / out_peer_rows, row dst % out_peer_rows
+  // of that peer's [rows, H_total, D] buffer (pointers pre-offset to my first head; out_sh / out_ss describe that layout)
+  uint16_t* out_peer[BLADE_MAX_PEERS];
+  int out_peer_rows;  // 0 = off
   long long* trace;  // BLADE_TRACE builds: clock64 stamps of CTA 0 (tools/trace_attn.py)
 };
 
@@ -709,7 +713,15 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           };
           if (!it.merge) weights(1.f);
-          uint16_t* orow = store ? p.out + b * p.out_sb + h * p.out_sh + static_cast<int64_t>(dst) * p.out_ss : nullptr;
+          uint16_t* orow = nullptr;
+          if (store) {
+            if (p.out_peer_rows) {  // stores over NVLink, overlapped with the next tile's MMAs
+              const int pp = dst / p.out_peer_rows;
+              orow = p.out_peer[pp] + h * p.out_sh + static_cast<int64_t>(dst - pp * p.out_peer_rows) * p.out_ss;
+            } else {
+              orow = p.out + b * p.out_sb + h * p.out_sh + static_cast<int64_t>(dst) * p.out_ss;
+            }
+          }
           // output row pointers of the 4 lanes of my group (null = row beyond S): after the 4x4 transpose lane L
           // stores part L & 3 of each of them
           uint16_t* orow_j[4];
@@ -888,15 +900,15 @@ static long long* g_trace_buf = nullptr;
 static thread_local int g_sched_prezeroed = 0;  // blade_asa_forward zeroes the item counter ahead of the mask kernels
 void attn_sched_prezeroed() { g_sched_prezeroed = 1; }
 static thread_local int g_sub64_next = 0;  // set by blade_block_sparse_attn64_fwd / blade_asa_attn64_fwd for one launch
+void attn_next_sub64() { g_sub64_next = 1; }
 
 static int device_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[64] = {0};  // per device: one process may drive several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = n[dev & 63];
+  if (!c) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c;
 }
 
 // attention workspace: [0, 256) the item counter, then per CTA and stream one parked pooled-branch tile
@@ -911,7 +923,7 @@ static float round_host(float x, bool bf16) {
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
                 int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
-                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream, const BladePeers* peers) {
   // one-shot flags set by the callers for exactly this launch: consumed up front, so that an early error return
   // cannot leak them into the next call on this thread
   const bool sched_prezeroed = g_sched_prezeroed != 0;
@@ -1008,6 +1020,22 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   p.log_gap_r = pooled ? round_host(logf(round_host((float)sample_gap, bf)), bf) : 0.f;
   p.exact_merge = exact_merge;
   p.sub64 = sub64;
+  if (peers && peers->out[0]) {
+    BLADE_REQUIRE(peers->n_peers >= 1 && peers->n_peers <= BLADE_MAX_PEERS && peers->my_peer >= 0 &&
+                      peers->my_peer < peers->n_peers && peers->rows_per_peer >= 1 && B == 1,
+                  BLADE_ERR_ARG, "BladePeers: bad n_peers / my_peer / rows_per_peer (B must be 1)");
+    BLADE_REQUIRE(static_cast<int64_t>(peers->n_peers) * peers->rows_per_peer >= S, BLADE_ERR_SHAPE,
+                  "peers hold %lld output rows, sequence has %lld", (long long)peers->n_peers * peers->rows_per_peer,
+                  (long long)S);
+    for (int i = 0; i < peers->n_peers; ++i) {
+      BLADE_REQUIRE(peers->out[i] && (reinterpret_cast<uintptr_t>(peers->out[i]) & 15) == 0, BLADE_ERR_ARG,
+                    "peer %d: output pointer null or misaligned", i);
+      p.out_peer[i] = static_cast<uint16_t*>(peers->out[i]) + static_cast<int64_t>(peers->my_peer) * H * D;
+    }
+    p.out_peer_rows = peers->rows_per_peer;
+    p.out_sh = D;                                       // [rows, H_total, D] token-major
+    p.out_ss = static_cast<int64_t>(peers->n_peers) * H * D;
+  }
 #ifdef BLADE_TRACE
   {
     static long long* tbuf = nullptr;  // debug build only (tools/trace_attn.py); the product never allocates
@@ -1061,7 +1089,7 @@ extern "C" int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTens
                                            BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
                                            void* workspace, size_t ws_bytes, void* stream) {
   return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
-                     ws_bytes, static_cast<cudaStream_t>(stream));
+                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 // block_size 64 variants: idx entries = (128-key tile id) | (quadrant mask << 28), built by blade_mask64_to_index
@@ -1071,7 +1099,7 @@ extern "C" int blade_block_sparse_attn64_fwd(const BladeTensor* q, const BladeTe
                                              void* workspace, size_t ws_bytes, void* stream) {
   g_sub64_next = 1;
   return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
-                     ws_bytes, static_cast<cudaStream_t>(stream));
+                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
 }
 extern "C" int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                                     const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool,
@@ -1081,7 +1109,7 @@ extern "C" int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, 
   BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
   g_sub64_next = 1;
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
-                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
@@ -1091,7 +1119,7 @@ extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, co
                                   size_t ws_bytes, void* stream) {
   BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
-                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 #ifdef BLADE_TRACE

@@ -17,16 +17,18 @@ char* last_error_buf() {
 }
 
 StageEvents* stage_events() {
-  static StageEvents ev[4] = {};
+  static thread_local StageEvents ev[5] = {};  // measurement hook: per calling thread, like the launches it brackets
   return ev;
 }
 
 size_t attn_park_bytes(int64_t D);
 void attn_sched_prezeroed();
+void attn_next_sub64();
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
                 int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
-                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                const BladePeers* peers = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // Generalised Hilbert curve (the algorithm of gilbert3d.py:6-167), iterative, integer 3-vectors.
@@ -122,7 +124,8 @@ static ForkState* fork_state() {
 
 // workspace carving for blade_asa_forward
 struct ForwardWs {
-  size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, rstd, total;
+  size_t q_r, k_r, v_r, q_mean, k_mean, k_pool, v_pool, scores, idx, cnt, park, rstd, q_s, k_s, mask64, idx128, cnt128,
+      total;
 };
 static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAsaConfig* cfg) {
   ForwardWs w{};
@@ -147,6 +150,16 @@ static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAs
   w.cnt = take(B * H * nb * 4);
   w.park = take(attn_park_bytes(D));
   w.rstd = take(2 * B * S * 4);  // q/k RMSNorm statistic (BladeQkNorm)
+  if (cfg->estimator == 1) {     // sampled-max estimator: the num_keep sampled rows of every block (W:37-60)
+    w.q_s = take(B * H * nb * 32 * D * 2);
+    w.k_s = take(B * H * nb * 32 * D * 2);
+  }
+  if (blk == 64) {               // 64-granular selection feeding the 128x128 tensor-core tiles
+    const int64_t n128 = ceil_div(nb, 2);
+    w.mask64 = take(B * H * nb * nb);
+    w.idx128 = take(B * H * n128 * n128 * 4);
+    w.cnt128 = take(B * H * n128 * 4);
+  }
   w.total = off;
   return w;
 }
@@ -155,11 +168,14 @@ static ForwardWs carve(int64_t B, int64_t H, int64_t S, int64_t D, const BladeAs
 
 using namespace blade;
 
+static_assert(sizeof(BladeAsaConfig) == 104 && sizeof(BladeTensor) == 80 && sizeof(BladePeers) == 16 + 4 * 8 * BLADE_MAX_PEERS,
+              "C ABI struct layout changed: bump BLADE_ABI_VERSION and the ctypes mirrors in video_blade_b200/_lib.py");
+
 extern "C" int blade_abi_version(void) { return BLADE_ABI_VERSION; }
 extern "C" const char* blade_last_error(void) { return last_error_buf(); }
 
 extern "C" int blade_profile_events(int32_t stage, void* start_event, void* stop_event) {
-  BLADE_REQUIRE(stage >= 0 && stage < 4, BLADE_ERR_ARG, "stage %d out of range", stage);
+  BLADE_REQUIRE(stage >= 0 && stage < 5, BLADE_ERR_ARG, "stage %d out of range", stage);
   stage_events()[stage].start = static_cast<cudaEvent_t>(start_event);
   stage_events()[stage].stop = static_cast<cudaEvent_t>(stop_event);
   return BLADE_OK;
@@ -205,10 +221,15 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BLADE_REQUIRE(cfg, BLADE_ERR_ARG, "cfg null");
   if (int e = check_tensor16(q, "q")) return e;
-  BLADE_REQUIRE(cfg->block_size == 128, BLADE_ERR_ARG,
-                "blade_asa_forward: attention block size is 128 (W:325); got %d", cfg->block_size);
-  BLADE_REQUIRE(cfg->estimator == 0 || scores_in, BLADE_ERR_ARG, "estimator %d not available in this entry point",
+  BLADE_REQUIRE(cfg->block_size == 128 || cfg->block_size == 64, BLADE_ERR_ARG,
+                "blade_asa_forward: block size %d not in {64, 128} (W:325)", cfg->block_size);
+  BLADE_REQUIRE(cfg->estimator == 0 || cfg->estimator == 1, BLADE_ERR_ARG, "estimator %d not in {0 = mean-pool, 1 = sampled-max}",
                 cfg->estimator);
+  const bool sampled = cfg->estimator == 1 && !scores_in;
+  BLADE_REQUIRE(!sampled || (cfg->sample_q_off && cfg->sample_k_off), BLADE_ERR_ARG,
+                "estimator 1 (sampled-max, W:62-87) needs cfg->sample_q_off / sample_k_off (device int32 [B,H,32])");
+  BLADE_REQUIRE(!sampled || cfg->num_keep == 32, BLADE_ERR_ARG, "the sampled estimator is built for num_keep = 32 (W:62)");
+  const bool blk64 = cfg->block_size == 64;
   const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
   const ForwardWs w = carve(B, H, S, D, cfg);
   BLADE_REQUIRE(workspace && ws_bytes >= w.total, BLADE_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
@@ -218,7 +239,8 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   const int64_t nb = ceil_div(S, cfg->block_size);
   const int64_t np = cfg->sample_gap > 0 ? ceil_div(S, cfg->sample_gap) : 0;
   const bool norm_on = cfg->qk_norm != nullptr && cfg->qk_norm->kind != 0;
-  const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr || norm_on;  // these need the output copies
+  const bool pull = cfg->peers != nullptr && cfg->peers->q[0] != nullptr;  // q/k/v rows live in the peers' memory
+  const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr || norm_on || pull;  // these need the output copies
   PrepNorm pn{};
   if (norm_on) {
     pn.kind = cfg->qk_norm->kind;
@@ -239,12 +261,12 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   // the attention kernel's item counter (head of its workspace) is zeroed here, ahead of the mask kernels, so the
   // memset is not on the path between the selection and the attention launch
   BLADE_CUDA_OK(cudaMemsetAsync(ws + w.park, 0, sizeof(int), stream));
-  const bool need_means = scores_in == nullptr;
+  const bool need_means = scores_in == nullptr && !sampled;
   // gather / rotate / block means on the caller's stream ...
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
                         rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
-                        stream, norm_on ? &pn : nullptr, cfg->token_row))
+                        stream, norm_on ? &pn : nullptr, cfg->token_row, cfg->peers))
     return e;
   // ... then the bandwidth-bound gap pooling and the latency-bound score + selection kernels run concurrently on
   // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):
@@ -264,20 +286,6 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   };
   if (np && fork_mode != 1)
     if (int e = run_pool()) return e;
-  const float* sc = scores_in;
-  if (!sc) {
-    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, mstream)) return e;
-    sc = scores;
-  } else if (scores_out) {
-    BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, mstream));
-  }
-  if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, mstream)) return e;
-  if (np && fork_mode == 1)
-    if (int e = run_pool()) return e;
-  if (fk) {
-    BLADE_CUDA_OK(cudaEventRecord(fk->join, fk->side));
-    BLADE_CUDA_OK(cudaStreamWaitEvent(stream, fk->join, 0));
-  }
   BladeTensor qr = *q, kr = *k, vr = *v;
   if (rearr) {
     const int64_t cs[4] = {H * S * D, S * D, D, 1};
@@ -285,6 +293,46 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     kr.ptr = ws + w.k_r;
     vr.ptr = ws + w.v_r;
     for (int i = 0; i < 4; ++i) qr.stride[i] = kr.stride[i] = vr.stride[i] = cs[i];
+  }
+  const float* sc = scores_in;
+  if (sampled) {
+    // the reference's estimator (efficient_attn_with_pooling, W:62-87 -> P:201-253) on the gathered / rotated /
+    // normalised q and k: sample num_keep rows per block, then the tcgen05 score kernel
+    if (int e = blade_asa_sample_tokens(&qr, &kr, cfg->sample_q_off, cfg->sample_k_off, ws + w.q_s, ws + w.k_s,
+                                        cfg->block_size, mstream))
+      return e;
+    if (int e = blade_asa_scores_sampled(ws + w.q_s, ws + w.k_s, scores, B, H, nb, D, q->dtype, mstream)) return e;
+    sc = scores;
+  } else if (!sc) {
+    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, mstream)) return e;
+    sc = scores;
+  } else if (scores_out) {
+    BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, mstream));
+  }
+  const int32_t* attn_idx = idx;
+  const int32_t* attn_cnt = cnt;
+  int64_t attn_stride = nb;
+  if (blk64) {
+    // block_size 64 (BASELINE config 1): select on the 64-granular score map, then fold the bool mask into
+    // quadrant-flagged lists over the 128x128 tensor-core tiles.  cnt_out = the 64-granular counts [B,H,nb];
+    // idx_out (if given) = the 128-tile lists [B,H,ceil(nb/2),ceil(nb/2)].
+    uint8_t* m64 = mask_out ? mask_out : ws + w.mask64;
+    int32_t* i64 = reinterpret_cast<int32_t*>(ws + w.idx);
+    int32_t* i128 = idx_out ? idx_out : reinterpret_cast<int32_t*>(ws + w.idx128);
+    int32_t* c128 = reinterpret_cast<int32_t*>(ws + w.cnt128);
+    if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, i64, cnt, m64, nullptr, mstream)) return e;
+    if (int e = blade_mask64_to_index(m64, B, H, nb, nb, i128, c128, mstream)) return e;
+    attn_idx = i128;
+    attn_cnt = c128;
+    attn_stride = ceil_div(nb, 2);
+  } else {
+    if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, mstream)) return e;
+  }
+  if (np && fork_mode == 1)
+    if (int e = run_pool()) return e;
+  if (fk) {
+    BLADE_CUDA_OK(cudaEventRecord(fk->join, fk->side));
+    BLADE_CUDA_OK(cudaStreamWaitEvent(stream, fk->join, 0));
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   if (np) {
@@ -299,10 +347,12 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     }
     kp.dtype = vp.dtype = q->dtype;
     attn_sched_prezeroed();
-    return launch_attn(&qr, &kr, &vr, idx, cnt, nb, &kp, &vp, cfg->sample_gap, out, nullptr, dst_row, scale,
-                       cfg->exact_merge, ws + w.park, attn_park_bytes(D), stream);
+    if (blk64) attn_next_sub64();
+    return launch_attn(&qr, &kr, &vr, attn_idx, attn_cnt, attn_stride, &kp, &vp, cfg->sample_gap, out, nullptr, dst_row,
+                       scale, cfg->exact_merge, ws + w.park, attn_park_bytes(D), stream, cfg->peers);
   }
   attn_sched_prezeroed();
-  return launch_attn(&qr, &kr, &vr, idx, cnt, nb, nullptr, nullptr, 0, out, nullptr, dst_row, scale, 0, ws + w.park,
-                     attn_park_bytes(D), stream);
+  if (blk64) attn_next_sub64();
+  return launch_attn(&qr, &kr, &vr, attn_idx, attn_cnt, attn_stride, nullptr, nullptr, 0, out, nullptr, dst_row, scale, 0,
+                     ws + w.park, attn_park_bytes(D), stream, cfg->peers);
 }

@@ -32,11 +32,11 @@ inline int fail(int code, const char* fmt, ...) {
     if (!(cond)) return ::blade::fail(code, __VA_ARGS__); \
   } while (0)
 
-// optional profiling events (blade_profile_events): stage 0 prep, 1 scores, 2 select, 3 attention
+// optional profiling events (blade_profile_events): stage 0 prep, 1 scores, 2 select, 3 attention, 4 gap pooling
 struct StageEvents {
   cudaEvent_t start, stop;
 };
-StageEvents* stage_events();  // array of 4 (defined in capi.cu)
+StageEvents* stage_events();  // array of 5 (defined in capi.cu)
 struct StageTimer {
   int stage;
   cudaStream_t stream;
@@ -62,8 +62,9 @@ struct PrepNorm {
 int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
               int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream,
-              const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr);
-int rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream);
+              const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr, const BladePeers* peers = nullptr);
+int rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream,
+                  float* const* peer_out = nullptr, int n_peers = 0, int64_t out_rows = 0, int64_t out_row0 = 0);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -64,15 +64,67 @@ struct Strides3 {
   int64_t b, h, s;  // element strides
 };
 
+// BladeAsaConfig.select_rounding: 0 = fp32 scores; 1 = bf16, 2 = f16 (the reference keeps Po in the model dtype, W:214-221)
+__device__ __forceinline__ float round_sel(float x, int mode) {
+  if (mode == 1) return __bfloat162float(__float2bfloat16_rn(x));
+  if (mode == 2) return __half2float(__float2half_rn(x));
+  return x;
+}
+// The cut of transfer_attn_to_mask(mode="energy") over the descending-sorted row `sorted[0..nk)` (fp64 copies of the
+// fp32 values): first index whose prefix sum reaches energy_threshold * total, exclusive (W:217-224); nk if none below
+// `lim`.  Sequential on purpose: bit-exact with torch's CPU cumsum, which accumulates fp32 inputs in fp64 and 16-bit
+// inputs in fp32, rounding every emitted prefix to the tensor dtype.
+__device__ __forceinline__ int energy_cut(const double* sorted, int nk, int lim, float thr, int mode) {
+  if (mode == 0) {
+    double acc = 0.0;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 8 <= nk; i += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = sorted[i + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += t[u];
+    }
+    for (; i < nk; ++i) acc += sorted[i];
+    const float th = __fmul_rn(thr, static_cast<float>(acc));
+    acc = 0.0;
+    for (i = 0; i < lim; ++i) {
+      acc += sorted[i];
+      if (static_cast<float>(acc) >= th) return i;
+    }
+    return nk;
+  }
+  float acc = 0.f;
+  for (int i = 0; i < nk; ++i) acc = __fadd_rn(acc, static_cast<float>(sorted[i]));
+  const float th = round_sel(__fmul_rn(thr, round_sel(acc, mode)), mode);
+  acc = 0.f;
+  for (int i = 0; i < lim; ++i) {
+    acc = __fadd_rn(acc, static_cast<float>(sorted[i]));
+    if (round_sel(acc, mode) >= th) return i;
+  }
+  return nk;
+}
+
 // ------------------------------------------------------------------------------------------------
 // q/k RMSNorm statistic (Wan: rms_norm_across_heads, MW:99-102): rstd[token] = rsqrt(mean over all H*D channels of
 // x^2 + eps) for q and k.  One warp per token row ([B,S,H*D] memory, a contiguous 2*H*D-byte segment), 16-byte loads.
 // out: fp32 [2][B*S] (q then k).  The normalisation itself happens inside prep_block_kernel.
 // ------------------------------------------------------------------------------------------------
+// Ulysses push variant: the statistic of MY token shard goes to every peer's full-length [2][out_rows] table at row
+// offset out_row0 (stores over NVLink; the caller's barrier publishes them)
+struct StatPeers {
+  float* out[BLADE_MAX_PEERS];
+  int n;            // 0 = single destination `out`
+  int64_t out_rows; // rows of a destination table (tokens of the whole sequence)
+  int64_t out_row0; // first row I own
+};
+
 template <bool IS_BF16>
 __global__ void __launch_bounds__(256) rms_stat_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
                                                        int64_t q_sb, int64_t q_ss, int64_t k_sb, int64_t k_ss, int S,
-                                                       int64_t rows, int hd, float eps, float* __restrict__ out) {
+                                                       int64_t rows, int hd, float eps, float* __restrict__ out,
+                                                       const StatPeers peers) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
@@ -89,13 +141,25 @@ __global__ void __launch_bounds__(256) rms_stat_kernel(const uint16_t* __restric
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) out[t * rows + row] = rsqrtf(acc / static_cast<float>(hd) + eps);
+    const float r = rsqrtf(acc / static_cast<float>(hd) + eps);
+    if (peers.n == 0) {
+      if (lane == 0) out[t * rows + row] = r;
+    } else if (lane < peers.n) {
+      peers.out[lane][t * peers.out_rows + peers.out_row0 + row] = r;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // prep: grid (nb, H, B), 256 threads.  One CTA = one block of `block` output rows of one head.
 // ------------------------------------------------------------------------------------------------
+// Ulysses pull: token t of tensor j lives on peer t / rows at local row t % rows of that peer's [rows, H_total, D]
+// projection output; base[j][p] already points at my first head's channels (BladePeers)
+struct PeerSrc {
+  const uint16_t* base[3][BLADE_MAX_PEERS];
+  int rows;  // 0 = off
+};
+
 template <int D, bool IS_BF16, bool COPY, bool ROPE, bool NORM>
 __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
                                                          const uint16_t* __restrict__ v, Strides3 sq, Strides3 sk,
@@ -108,7 +172,7 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
                                                          const uint16_t* __restrict__ wk, int norm_kind,
                                                          const int32_t* __restrict__ tok_row,
                                                          const uint16_t* __restrict__ bq, const uint16_t* __restrict__ bk,
-                                                         float norm_eps) {
+                                                         float norm_eps, const __grid_constant__ PeerSrc peer) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -148,7 +212,16 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
         const int rc = r < S ? r : S - 1;  // replicate padding (W:35)
         const int sr = src_row ? __ldg(src_row + rc) : rc;
         srcs[u] = ((ROPE || NORM) && tok_row) ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
-        if (p < passes) val[u] = ldg_stream(reinterpret_cast<const uint4*>(base + sr * st.s) + chunk);
+        if (p < passes) {
+          const uint16_t* rowp;
+          if (peer.rows) {  // uniform: pull the row over NVLink from the peer that owns token sr
+            const int pp = sr / peer.rows;
+            rowp = peer.base[t][pp] + h * st.h + static_cast<int64_t>(sr - pp * peer.rows) * st.s;
+          } else {
+            rowp = base + sr * st.s;
+          }
+          val[u] = ldg_stream(reinterpret_cast<const uint4*>(rowp) + chunk);
+        }
       }
       if (NORM && t < 2 && norm_kind == 3) {
         // CogVideoX: LayerNorm over the D channels of this head (MC:54-57); a row is spread over LPR lanes
@@ -429,7 +502,8 @@ __global__ void __launch_bounds__(256) select_rank_kernel(const float* __restric
                                                           int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
                                                           const int32_t* __restrict__ hi_bh, float thr, int force_last,
                                                           int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
-                                                          uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
+                                                          uint8_t* __restrict__ mask, int32_t* __restrict__ kcut,
+                                                          int rounding, unsigned long long* __restrict__ sel_acc) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk_pad = (nk + 31) & ~31;
@@ -463,17 +537,30 @@ __global__ void __launch_bounds__(256) select_rank_kernel(const float* __restric
   const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kfirst = nk;
   if (lane == 0) {
-    double acc = 0.0;
-    for (int i = 0; i < nk; ++i) acc += static_cast<double>(sorted[i]);
-    const float total = static_cast<float>(acc);
-    const float th = __fmul_rn(thr, total);
-    acc = 0.0;
     const int lim = hi < nk ? hi : nk;  // beyond `hi` the clamp decides
-    for (int i = 0; i < lim; ++i) {
-      acc += static_cast<double>(sorted[i]);
-      if (static_cast<float>(acc) >= th) {
-        kfirst = i;
-        break;
+    if (rounding == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < nk; ++i) acc += static_cast<double>(sorted[i]);
+      const float th = __fmul_rn(thr, static_cast<float>(acc));
+      acc = 0.0;
+      for (int i = 0; i < lim; ++i) {
+        acc += static_cast<double>(sorted[i]);
+        if (static_cast<float>(acc) >= th) {
+          kfirst = i;
+          break;
+        }
+      }
+    } else {
+      float acc = 0.f;
+      for (int i = 0; i < nk; ++i) acc = __fadd_rn(acc, sorted[i]);
+      const float th = round_sel(__fmul_rn(thr, round_sel(acc, rounding)), rounding);
+      acc = 0.f;
+      for (int i = 0; i < lim; ++i) {
+        acc = __fadd_rn(acc, sorted[i]);
+        if (round_sel(acc, rounding) >= th) {
+          kfirst = i;
+          break;
+        }
       }
     }
   }
@@ -495,7 +582,10 @@ __global__ void __launch_bounds__(256) select_rank_kernel(const float* __restric
     base += __popc(bal);
   }
   for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
-  if (lane == 0) cnt[row] = base;
+  if (lane == 0) {
+    cnt[row] = base;
+    if (sel_acc) atomicAdd(sel_acc, static_cast<unsigned long long>(base));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +601,8 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
                                                              int nk, int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
                                                              const int32_t* __restrict__ hi_bh, float thr, int force_last,
                                                              int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
-                                                             uint8_t* __restrict__ mask, int32_t* __restrict__ kcut) {
+                                                             uint8_t* __restrict__ mask, int32_t* __restrict__ kcut,
+                                                             int rounding, unsigned long long* __restrict__ sel_acc) {
   constexpr int N = 32 * E;
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -582,32 +673,7 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
   const int lo = lo_bh ? lo_bh[bh] : lo_s;
   const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kfirst = nk;
-  if (lane == 0) {
-    // sequential on purpose (bit-exact with torch's CPU cumsum); the loads are independent of the add chain,
-    // so unrolling lets them run ahead.  Padding entries are -inf only beyond nk and are never added.
-    double acc = 0.0;
-    int i = 0;
-#pragma unroll 1
-    for (; i + 8 <= nk; i += 8) {
-      double t[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = sorted[i + u];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc += t[u];
-    }
-    for (; i < nk; ++i) acc += sorted[i];
-    const float total = static_cast<float>(acc);
-    const float th = __fmul_rn(thr, total);
-    acc = 0.0;
-    const int lim = hi < nk ? hi : nk;                       // beyond `hi` the clamp decides
-    for (i = 0; i < lim; ++i) {
-      acc += sorted[i];
-      if (static_cast<float>(acc) >= th) {
-        kfirst = i;
-        break;
-      }
-    }
-  }
+  if (lane == 0) kfirst = energy_cut(sorted, nk, hi < nk ? hi : nk /* beyond `hi` the clamp decides */, thr, rounding);
   kfirst = __shfl_sync(0xffffffffu, kfirst, 0);
   int kc = kfirst < lo ? lo : kfirst;
   kc = kc > hi ? hi : kc;
@@ -631,7 +697,10 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
     base += __popc(bal);
   }
   for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
-  if (lane == 0) cnt[row] = base;
+  if (lane == 0) {
+    cnt[row] = base;
+    if (sel_acc) atomicAdd(sel_acc, static_cast<unsigned long long>(base));
+  }
 }
 
 __global__ void __launch_bounds__(256) mask_to_index_kernel(const uint8_t* __restrict__ mask, int64_t total_rows, int nk,
@@ -711,10 +780,23 @@ extern "C" int blade_asa_prep_rope(const BladeTensor* q, const BladeTensor* k, c
                           rope_cos_sin, rope_first_row, 3, static_cast<cudaStream_t>(stream_));
 }
 
-int blade::rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream) {
+int blade::rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream,
+                         float* const* peer_out, int n_peers, int64_t out_rows, int64_t out_row0) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
-  BLADE_REQUIRE(out, BLADE_ERR_ARG, "rstd output null");
+  BLADE_REQUIRE(out || (peer_out && n_peers > 0), BLADE_ERR_ARG, "rstd output null");
+  BLADE_REQUIRE(n_peers >= 0 && n_peers <= BLADE_MAX_PEERS, BLADE_ERR_ARG, "n_peers %d out of range", n_peers);
+  StatPeers sp{};
+  if (peer_out && n_peers > 0) {
+    sp.n = n_peers;
+    sp.out_rows = out_rows;
+    sp.out_row0 = out_row0;
+    for (int i = 0; i < n_peers; ++i) {
+      BLADE_REQUIRE(peer_out[i], BLADE_ERR_ARG, "peer rstd table %d null", i);
+      sp.out[i] = peer_out[i];
+    }
+    BLADE_REQUIRE(q->shape[0] == 1 && out_row0 + q->shape[2] <= out_rows, BLADE_ERR_SHAPE, "peer rstd rows out of range");
+  }
   const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
   for (const BladeTensor* t : {q, k}) {
     BLADE_REQUIRE(t->shape[0] == B && t->shape[1] == H && t->shape[2] == S && t->shape[3] == D && t->dtype == q->dtype,
@@ -728,10 +810,10 @@ int blade::rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, 
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr);
   if (q->dtype == BLADE_BF16)
     rms_stat_kernel<true><<<grid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
-                                                    static_cast<int>(S), rows, static_cast<int>(H * D), eps, out);
+                                                    static_cast<int>(S), rows, static_cast<int>(H * D), eps, out, sp);
   else
     rms_stat_kernel<false><<<grid, 256, 0, stream>>>(qp, kp, q->stride[0], q->stride[2], k->stride[0], k->stride[2],
-                                                     static_cast<int>(S), rows, static_cast<int>(H * D), eps, out);
+                                                     static_cast<int>(S), rows, static_cast<int>(H * D), eps, out, sp);
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
 }
@@ -740,11 +822,18 @@ extern "C" int blade_qk_rms_stat(const BladeTensor* q, const BladeTensor* k, flo
   return blade::rms_stat_impl(q, k, eps, rstd_out, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int blade_qk_rms_stat_peers(const BladeTensor* q, const BladeTensor* k, float eps, float* const* rstd_peers,
+                                       int32_t n_peers, int64_t total_rows, int64_t first_row, void* stream) {
+  return blade::rms_stat_impl(q, k, eps, nullptr, static_cast<cudaStream_t>(stream), rstd_peers, n_peers, total_rows,
+                              first_row);
+}
+
 // parts: bit 0 = gather/copy/means kernel, bit 1 = gap-pooling kernel (reads the copies when they exist)
 int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
                      void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool,
                      int32_t block_size, int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row,
-                     int parts, cudaStream_t stream, const PrepNorm* norm, const int32_t* tok_row) {
+                     int parts, cudaStream_t stream, const PrepNorm* norm, const int32_t* tok_row,
+                     const BladePeers* peers) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -757,6 +846,27 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   BLADE_REQUIRE(S >= 1 && B >= 1 && H >= 1 && H <= 65535 && B <= 65535, BLADE_ERR_SHAPE, "bad B/H/S");
   const bool copy = q_r || k_r || v_r;
   BLADE_REQUIRE(!copy || (q_r && k_r && v_r), BLADE_ERR_ARG, "q_r/k_r/v_r must be all set or all NULL");
+  PeerSrc psrc{};
+  if (peers && peers->q[0]) {
+    BLADE_REQUIRE(peers->n_peers >= 1 && peers->n_peers <= BLADE_MAX_PEERS && peers->my_peer >= 0 &&
+                      peers->my_peer < peers->n_peers && peers->rows_per_peer >= 1,
+                  BLADE_ERR_ARG, "BladePeers: bad n_peers / my_peer / rows_per_peer");
+    BLADE_REQUIRE(B == 1 && copy, BLADE_ERR_ARG, "peer pull needs B == 1 and the gathered copies");
+    BLADE_REQUIRE(static_cast<int64_t>(peers->n_peers) * peers->rows_per_peer >= S, BLADE_ERR_SHAPE,
+                  "peers hold %lld rows, sequence has %lld", (long long)peers->n_peers * peers->rows_per_peer, (long long)S);
+    const int64_t h_total = static_cast<int64_t>(peers->n_peers) * H;
+    for (const BladeTensor* t : {q, k, v})
+      BLADE_REQUIRE(t->stride[1] == D && t->stride[2] == h_total * D, BLADE_ERR_SHAPE,
+                    "peer pull: q/k/v must describe [rows, n_peers*H, D] token-major memory");
+    for (int i = 0; i < peers->n_peers; ++i) {
+      BLADE_REQUIRE(peers->q[i] && peers->k[i] && peers->v[i], BLADE_ERR_ARG, "peer %d: q/k/v pointer null", i);
+      const int64_t off = static_cast<int64_t>(peers->my_peer) * H * D;
+      psrc.base[0][i] = static_cast<const uint16_t*>(peers->q[i]) + off;
+      psrc.base[1][i] = static_cast<const uint16_t*>(peers->k[i]) + off;
+      psrc.base[2][i] = static_cast<const uint16_t*>(peers->v[i]) + off;
+    }
+    psrc.rows = peers->rows_per_peer;
+  }
   BLADE_REQUIRE(copy || !src_row, BLADE_ERR_ARG, "src_row given but no output copies requested");
   BLADE_REQUIRE(copy || !rope_cos_sin, BLADE_ERR_ARG, "rotary embedding needs the q_r/k_r/v_r outputs");
   BLADE_REQUIRE(!rope_cos_sin || (reinterpret_cast<uintptr_t>(rope_cos_sin) & 15) == 0, BLADE_ERR_ALIGN,
@@ -765,7 +875,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   const bool bf = q->dtype == BLADE_BF16;
   Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
       sv{v->stride[0], v->stride[1], v->stride[2]};
-  StageTimer timer(parts == 2 ? -1 : 0, stream);
+  StageTimer timer(parts == 2 ? 4 : 0, stream);
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
   const float* rstd = nullptr;
@@ -798,7 +908,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   prep_block_kernel<DD, BF, CP, RP, NM><<<grid, 256, 0, stream>>>(                                                    \
       qp, kp, vp, sq, sk, sv, src_row, static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r),                      \
       static_cast<uint16_t*>(v_r), q_mean, k_mean, static_cast<int>(S), static_cast<int>(H), nb, block_size,          \
-      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps)
+      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps, psrc)
 #define LAUNCH_PREP_B(DD, CP, RP, NM)                                                                                 \
   do {                                                                                                                \
     if (bf) LAUNCH_PREP(DD, true, CP, RP, NM); else LAUNCH_PREP(DD, false, CP, RP, NM);                               \
@@ -863,6 +973,8 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
   BLADE_REQUIRE(scores && idx && cnt && cfg, BLADE_ERR_ARG, "null pointer");
   BLADE_REQUIRE(nq >= 1 && nk >= 1 && nk <= 4096, BLADE_ERR_SHAPE, "bad nq/nk");
   BLADE_REQUIRE(cfg->min_retain >= 1 && cfg->max_retain >= 1, BLADE_ERR_ARG, "retain bounds must be >= 1");
+  BLADE_REQUIRE(cfg->select_rounding >= 0 && cfg->select_rounding <= 2, BLADE_ERR_ARG, "select_rounding %d not in {0,1,2}",
+                cfg->select_rounding);
   const int64_t rows = B * H * nq;
   const int nk_pad = static_cast<int>((nk + 31) & ~31);
   const size_t smem = 8 * 2 * nk_pad * sizeof(float);
@@ -872,7 +984,7 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
     const size_t sm_b = 8 * (2 * 32 * EE) * sizeof(double);                                                           \
     select_bitonic_kernel<EE><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, sm_b, stream>>>(                    \
         scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,     \
-        cfg->force_last, idx, cnt, mask_opt, kcut_opt);                                                            \
+        cfg->force_last, idx, cnt, mask_opt, kcut_opt, cfg->select_rounding, cfg->selected_acc);                   \
   } while (0)
   if (nk <= 32) LAUNCH_BITONIC(1);
   else if (nk <= 64) LAUNCH_BITONIC(2);
@@ -883,7 +995,7 @@ extern "C" int blade_asa_select(const float* scores, int64_t B, int64_t H, int64
       BLADE_CUDA_OK(cudaFuncSetAttribute(select_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_rank_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, smem, stream>>>(
         scores, rows, (int)nq, (int)nk, cfg->min_retain, cfg->max_retain, lo_bh, hi_bh, cfg->energy_threshold,
-        cfg->force_last, idx, cnt, mask_opt, kcut_opt);
+        cfg->force_last, idx, cnt, mask_opt, kcut_opt, cfg->select_rounding, cfg->selected_acc);
   }
 #undef LAUNCH_BITONIC
   BLADE_CUDA_OK(cudaGetLastError());

@@ -35,10 +35,39 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
     the normalisation (my heads' weight slice), the rotary embedding and the curve-order gather all happen inside the
     gather kernel, reading the packed receive buffer in place."""
 
-    def __init__(self, group: Optional[UlyssesGroup], fuse: bool = True):
+    def __init__(self, group: Optional[UlyssesGroup], fuse: bool = True, plane=None):
         super().__init__()
         self.group = group
         self.fuse = fuse
+        self.plane = plane          # UlyssesPeerPlane: the exchange as NVLink loads/stores inside the layer's kernels
+
+    def _call_peer_plane(self, attn, hidden_states, rotary_emb):
+        """Peer-memory data plane: the projections write into the symmetric q/k/v buffer, the RMSNorm statistic of my
+        tokens is stored into every peer's table, and the layer pulls / pushes rows over NVLink (UlyssesPeerPlane)."""
+        from . import wanx_blocksparseattn as W
+        from .modify_wan import _rms_kind, _rope_table
+        pl, g = self.plane, self.group
+        eng = W._engine(use_rearrange=bool(attn.inner_attention.use_rearrange))
+        Hl, D = pl.Hl, pl.D
+        sl = slice(g.rank_in_group * Hl * D, (g.rank_in_group + 1) * Hl * D)           # my heads' weights
+        outs = []
+        for b in range(hidden_states.shape[0]):
+            x = hidden_states[b]
+            for j, lin in enumerate((attn.to_q, attn.to_k, attn.to_v)):
+                dst = pl.qkv[j].view(pl.Sl, pl.H * D)
+                if lin.bias is not None:
+                    torch.addmm(lin.bias, x, lin.weight.t(), out=dst)
+                else:
+                    torch.mm(x, lin.weight.t(), out=dst)
+            pl.push_rms_stat(eng, attn.norm_q.eps)
+            o, cnt = pl.attention(eng, rope=(_rope_table(self._full_rope(rotary_emb)), 0),
+                                  qk_norm=(_rms_kind(attn.norm_q), attn.norm_q.weight.detach()[sl],
+                                           attn.norm_k.weight.detach()[sl], float(attn.norm_q.eps), pl.rstd.view(-1)),
+                                  selected_acc=attn.inner_attention.counter(x.device))
+            attn.inner_attention.count_call(cnt)
+            outs.append(o.reshape(1, pl.Sl, pl.H * D))
+        o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)          # len 1: to_out reads the symmetric buffer in place
+        return attn.to_out[1](attn.to_out[0](o.type_as(hidden_states)))
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
         if self.group is None or self.group.P == 1:
@@ -47,6 +76,9 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
         from .modify_wan import _norm_fusable, _rms_kind, _rope_table
         g = self.group
         B = hidden_states.shape[0]
+        if self.plane is not None and self.fuse and rotary_emb is not None and hidden_states.is_cuda \
+                and _norm_fusable(attn, hidden_states, True) and getattr(attn.inner_attention, "supports_fused_rope", False):
+            return self._call_peer_plane(attn, hidden_states, rotary_emb)
         q = attn.to_q(hidden_states).unflatten(2, (attn.heads, -1))                    # [B, S/P, H, D]
         k = attn.to_k(hidden_states).unflatten(2, (attn.heads, -1))
         v = attn.to_v(hidden_states).unflatten(2, (attn.heads, -1))
@@ -110,8 +142,9 @@ class UlyssesCogAttnProcessor:
             # per-head LayerNorm and the rotary embedding need nothing from other ranks: both run inside the gather
             # kernel on the packed receive buffer (my heads, all tokens); the projections travel untouched
             cos, sin = rope_full
-            key_ = (cos.data_ptr(), sin.data_ptr())
-            if self._table is None or self._table[0] != key_:
+            key_ = (cos, sin, cos._version, sin._version)   # held references, not bare addresses
+            if self._table is None or self._table[0][0] is not cos or self._table[0][1] is not sin \
+                        or self._table[0][2:] != key_[2:]:
                 self._table = (key_, torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(q.device, torch.float32).contiguous())
             nq, nk = attn.norm_q, attn.norm_k
             kw = dict(rotary=(self._table[1], int(text_len)),
@@ -202,10 +235,39 @@ class WanLikeDiT(nn.Module):
         self.group: Optional[UlyssesGroup] = None
         self._rope = {}
 
-    def set_sequence_parallel(self, group: Optional[UlyssesGroup]):
+    def set_sequence_parallel(self, group: Optional[UlyssesGroup], data_plane: str = "auto"):
+        """data_plane: "p2p" = NVLink peer-memory pull/push inside the layer's kernels (UlyssesPeerPlane, needs
+        torch symmetric memory between the group's GPUs), "nccl" = all_to_all around the layer, "auto" = p2p if the
+        peer mapping can be set up on every rank, else nccl."""
         self.group = group
+        self._plane_mode = data_plane
+        self._plane = None
+        self.data_plane_in_use = "none" if group is None or group.P == 1 else "nccl"
         for blk in self.blocks:
             blk.attn1.set_processor(UlyssesWanAttnProcessor(group))
+
+    def _ensure_plane(self, Sl, device, dtype):
+        """Lazily (the token count is known at the first forward) build ONE peer plane shared by all blocks."""
+        g = self.group
+        if g is None or g.P == 1 or self._plane_mode == "nccl" or self._plane is not None:
+            return
+        import torch.distributed as dist
+        from .ulysses import UlyssesPeerPlane
+        ok, plane = 1, None
+        try:
+            plane = UlyssesPeerPlane(g, Sl, self.heads, self.dim // self.heads, dtype=dtype, device=device)
+        except Exception as e:                                         # no peer mapping: fall back to NCCL everywhere
+            ok = 0
+            if self._plane_mode == "p2p":
+                raise
+            print(f"[video_blade_b200] peer-memory plane unavailable ({type(e).__name__}: {e}); using NCCL all_to_all")
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self._plane = plane if int(flag.item()) else False
+        if self._plane:
+            self.data_plane_in_use = "p2p"
+            for blk in self.blocks:
+                blk.attn1.get_processor().plane = self._plane
 
     def patchify(self, lat):                                   # [B,C,F,H,W] -> [B,S,C*p]
         B, C, Fr, H, W = lat.shape
@@ -237,6 +299,7 @@ class WanLikeDiT(nn.Module):
         g = self.group
         if g is not None and g.P > 1:                          # keep my S/P token shard
             sl = slice(g.rank_in_group * (S // g.P), (g.rank_in_group + 1) * (S // g.P))
+            self._ensure_plane(S // g.P, x.device, next(self.parameters()).dtype)
             for blk in self.blocks:                            # the fused gather rotates all tokens of my heads
                 blk.attn1.get_processor().full_rotary_emb = rope
             x, rope = x[:, sl], rope[:, :, sl]

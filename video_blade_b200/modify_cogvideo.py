@@ -64,8 +64,9 @@ class SageAttnCogVideoXAttnProcessor:
             if getattr(attn.inner_attention, "supports_fused_rope", False) and not attn.is_cross_attention \
                     and query.is_cuda and self.fuse_rope:
                 cos, sin = image_rotary_emb                                    # [Sv, D], repeat-interleaved pairs
-                key_ = (cos.data_ptr(), sin.data_ptr())
-                if self._table is None or self._table[0] != key_:
+                key_ = (cos, sin, cos._version, sin._version)   # held references, not bare addresses
+                if self._table is None or self._table[0][0] is not cos or self._table[0][1] is not sin \
+                        or self._table[0][2:] != key_[2:]:
                     tab = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(query.device, torch.float32).contiguous()
                     self._table = (key_, tab)
                 fused_rope = (self._table[1], text_seq_length)                 # video rows only

@@ -25,19 +25,21 @@ def apply_rotary_emb(hidden_states: torch.Tensor, freqs: torch.Tensor) -> torch.
     return torch.view_as_real(x * f).flatten(3, 4).type_as(hidden_states)
 
 
-_ROPE_TABLES = {}
+_ROPE_TABLES = []     # (freqs tensor held alive, its version counter, fp32 table)
 
 
 def _rope_table(freqs: torch.Tensor) -> torch.Tensor:
-    """complex rotary table [1,1,S,D/2] -> fp32 [S, D/2, 2] of (cos, sin), cached per tensor."""
-    key = (freqs.data_ptr(), tuple(freqs.shape), str(freqs.device))
-    t = _ROPE_TABLES.get(key)
-    if t is None:
-        f = freqs.reshape(freqs.shape[-2], freqs.shape[-1])
-        t = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous()
-        if len(_ROPE_TABLES) > 16:
-            _ROPE_TABLES.clear()
-        _ROPE_TABLES[key] = t
+    """complex rotary table [1,1,S,D/2] -> fp32 [S, D/2, 2] of (cos, sin), cached per tensor OBJECT: the entry keeps
+    the source tensor alive and checks its version counter, so a freed-and-reused address or an in-place update can
+    never return a stale table (a bare data_ptr key could)."""
+    for ref, ver, tab in _ROPE_TABLES:
+        if ref is freqs and ver == freqs._version:
+            return tab
+    f = freqs.reshape(freqs.shape[-2], freqs.shape[-1])
+    t = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous()
+    if len(_ROPE_TABLES) >= 8:
+        _ROPE_TABLES.pop(0)
+    _ROPE_TABLES.append((freqs, freqs._version, t))
     return t
 
 

@@ -8,10 +8,13 @@ import torch
 
 
 def synth_qkv(B, H, S, D, seed, dtype=torch.bfloat16, structured: float = 0.0,
-              grid: Optional[Tuple[int, int, int]] = None, text_length: int = 0):
+              grid: Optional[Tuple[int, int, int]] = None, text_length: int = 0, ramp: bool = False):
     """Gaussian q,k,v, optionally with the structured positional component of SURVEY 8(d):
     per head F ~ N(0,6^2) [3, D/2]; phase = x/W*F0 + y/H*F1 + z/T*F2 over raster coordinates;
-    base = [cos phase ; sin phase]; q = a*base + N(0,1), k = a*base + N(0,1), v ~ N(0,1)."""
+    base = [cos phase ; sin phase]; q = a*base + N(0,1), k = a*base + N(0,1), v ~ N(0,1).
+    `ramp`: the amplitude grows linearly with the frame index (a * z/T): early frames look Gaussian (the selection
+    saturates at max_retain), late frames are strongly structured (min_retain), the frames between cover the range --
+    the "mixed" bench input, whose per-row retained counts differ inside every head."""
     g = torch.Generator().manual_seed(seed)
     q = torch.randn(B, H, S, D, generator=g)
     k = torch.randn(B, H, S, D, generator=g)
@@ -26,8 +29,9 @@ def synth_qkv(B, H, S, D, seed, dtype=torch.bfloat16, structured: float = 0.0,
         Fq = torch.randn(H, 3, D // 2, generator=g) * 6.0
         phase = x[None, :, None] * Fq[:, 0:1] + y[None, :, None] * Fq[:, 1:2] + z[None, :, None] * Fq[:, 2:3]
         base = torch.cat([torch.cos(phase), torch.sin(phase)], dim=-1)       # [H, n_vid, D]
-        q[:, :, text_length:text_length + n_vid] += structured * base[None]
-        k[:, :, text_length:text_length + n_vid] += structured * base[None]
+        amp = structured * (z[None, :, None] if ramp else 1.0)
+        q[:, :, text_length:text_length + n_vid] += (amp * base)[None]
+        k[:, :, text_length:text_length + n_vid] += (amp * base)[None]
     return q.to(dtype), k.to(dtype), v.to(dtype)
 
 

@@ -52,6 +52,14 @@ class UlyssesGroup:
         B, Sl, H, D = q.shape
         assert B == 1 and H % self.P == 0
         P, Hl = self.P, H // self.P
+        if P == 1:
+            # degree 1: nothing to exchange (and `self.group` is None, i.e. the WORLD group -- an all_to_all here
+            # would mix the sequences of different CFG groups).  Same return contract: [1,H,S,D] views of the
+            # caller's token-major tensors and the identity row table.
+            key = (str(q.device), Sl)
+            if key not in self._vrow:
+                self._vrow[key] = torch.arange(Sl, dtype=torch.int32, device=q.device)
+            return q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), self._vrow[key], (q, k, v)
         send = torch.empty(P, 3, Sl, Hl, D, dtype=q.dtype, device=q.device)
         for j, x in enumerate((q, k, v)):
             send[:, j].copy_(x.view(Sl, P, Hl, D).permute(1, 0, 2, 3))
@@ -77,3 +85,78 @@ class UlyssesGroup:
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=self.group)                        # chunk p <- rank p's heads
         return recv.permute(1, 0, 2, 3).reshape(1, Sl, self.P * Hl, D)
+
+
+class UlyssesPeerPlane:
+    """The Ulysses exchange as loads and stores over NVLink peer memory instead of two all-to-alls (SURVEY.md 8e,
+    include/blade_asa.h: BladePeers).  Per rank and group, symmetric buffers (torch.distributed._symmetric_memory:
+    CUDA VMM allocations mapped into every peer of the group):
+
+        qkv  [3, Sl, H, D]   my token shard's q/k/v projections (the caller writes them here, e.g. addmm(out=...))
+        out  [Sl, H, D]      my token shard's attention output, every head -- written by the peers' epilogues
+        rstd [2, S]          Wan q/k RMSNorm statistic of ALL tokens -- every rank stores its shard into all peers
+
+    One layer = (rstd push) -> barrier -> blade_asa_forward(peers=...) -> barrier:
+      * the gather kernel PULLS its heads' rows of q, k, v from the owning peers (no pack, no send buffer, no NCCL);
+      * the attention epilogue PUSHES each finished 128-row tile to the peers that own those tokens while the tensor
+        cores run the next tile -- the return all-to-all disappears into the kernel.
+    The two barriers are `_SymmetricMemory.barrier` (a few-microsecond signal exchange on the current stream)."""
+
+    def __init__(self, group: UlyssesGroup, Sl: int, H: int, D: int, dtype=torch.bfloat16, device=None):
+        import torch.distributed._symmetric_memory as symm
+        assert group.P > 1 and H % group.P == 0
+        self.g, self.Sl, self.H, self.D = group, Sl, H, D
+        self.P, self.Hl, self.S = group.P, H // group.P, Sl * group.P
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        esz = torch.empty(0, dtype=dtype).element_size()
+        n_qkv, n_out, n_rstd = 3 * Sl * H * D * esz, Sl * H * D * esz, 2 * self.S * 4
+        off_out = (n_qkv + 1023) // 1024 * 1024
+        off_rstd = (off_out + n_out + 1023) // 1024 * 1024
+        total = off_rstd + n_rstd
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group.group)
+        assert self.hdl.world_size == self.P and self.hdl.rank == group.rank_in_group
+        self.qkv = self.buf[:n_qkv].view(dtype).view(3, Sl, H, D)
+        self.out = self.buf[off_out:off_out + n_out].view(dtype).view(Sl, H, D)
+        self.rstd = self.buf[off_rstd:off_rstd + n_rstd].view(torch.float32).view(2, self.S)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        from ._lib import BladePeers
+        import ctypes as C
+        pe = BladePeers()
+        pe.n_peers, pe.my_peer, pe.rows_per_peer = self.P, group.rank_in_group, Sl
+        for p in range(self.P):
+            pe.q[p] = ptrs[p]
+            pe.k[p] = ptrs[p] + Sl * H * D * esz
+            pe.v[p] = ptrs[p] + 2 * Sl * H * D * esz
+            pe.out[p] = ptrs[p] + off_out
+        self.peers = pe
+        self._rstd_ptrs = (C.c_void_p * self.P)(*[ptrs[p] + off_rstd for p in range(self.P)])
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def views(self):
+        """[1, Hl, S, D] layout descriptors of q/k/v for the engine (rows are pulled from the peers)."""
+        Hl, S, D, H = self.Hl, self.S, self.D, self.H
+        base = self.g.rank_in_group * Hl * D
+        return tuple(self.qkv[j].as_strided((1, Hl, S, D), (0, D, H * D, 1), self.qkv[j].storage_offset() + base)
+                     for j in range(3))
+
+    def push_rms_stat(self, eng, eps: float):
+        """rstd of my tokens (q and k, all heads: MW:99-102) stored into every peer's table."""
+        import ctypes as C
+        from ._lib import check, current_stream, tensor_desc
+        q = self.qkv[0].unsqueeze(0).transpose(1, 2)                    # [1, H, Sl, D] view of token-major memory
+        k = self.qkv[1].unsqueeze(0).transpose(1, 2)
+        check(eng.lib.blade_qk_rms_stat_peers(C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), float(eps),
+                                              self._rstd_ptrs, self.P, self.S, self.g.rank_in_group * self.Sl,
+                                              current_stream()))
+
+    def attention(self, eng, **kw):
+        """barrier -> layer (pull q/k/v, push out) -> barrier.  Returns my [Sl, H, D] output buffer (valid on the
+        current stream after the call)."""
+        self.barrier()                                                   # every peer's q/k/v (and rstd) are written
+        q, k, v = self.views()
+        _, cnt = eng.forward(q, k, v, peers=self.peers, **kw)
+        self.barrier()                                                   # every peer's output rows have landed
+        return self.out, cnt
