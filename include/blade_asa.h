@@ -262,6 +262,42 @@ int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTen
                       int32_t* idx_out, int32_t* cnt_out,
                       void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- f4: multi-level pooled sparse attention (the reference's experimental path) -------------------------------
+ * Reference (under cogvideox/sample_evaluate/Triton/): cogvideo_newattn.py (N) and the Triton kernels
+ * kernels/block_sparse_attn_kernel_with_backward_9_10.py (K9).  A block-mask entry is a LEVEL: 0 = skip, 1 = the
+ * block's 128 keys, L in {2,4,8} = its 128/L mean-pooled keys/values with `+ log L` on the scaled score; one softmax
+ * per query row (K9:135-277, 339-692).  Forward only (the backward, K9:695-1237, is not built).
+ *
+ *   reference interface                                           replaced by
+ *   pooling x3 over the padded K, V       (K9:1252-1270, 1307-1316)   blade_multilevel_pyramid
+ *   transfer_attn_to_mask(attn, ratios)   (N:154-207)                 blade_multilevel_mask
+ *   sparse_attention_fn(q,k,v,mask,None)  (K9:1578-1611 -> _fwd_kernel K9:339-692)
+ *                                                   blade_level_mask_to_index + blade_multilevel_attn_fwd
+ *
+ * blade_multilevel_pyramid: k,v [B,H,S,D] (any strides) -> contiguous k2,v2 [B,H,nb*64,D], k4,v4 [B,H,nb*32,D],
+ *   k8,v8 [B,H,nb*16,D] (nb = ceil(S/128)); every round of pair means is rounded to the tensor dtype.
+ * blade_multilevel_mask: scores fp32 [B,H,nq,nk] (nk <= 256); rank_level device u8 [nk]: level of the block ranked p-th
+ *   (value descending, index ascending) -- the host expands the reference's ratio table into it; the last force_last
+ *   rows and columns are set to level 1 (N:201-203).  Outputs: level_mask u8 [B,H,nq,nk] (optional), idx int32
+ *   [B,H,nq,nk] = the row's block ids sorted by (level, block id), -1 padded; cnt4 int32 [B,H,nq,4] = entries of level
+ *   1, 2, 4, 8 (16-byte aligned).
+ * blade_multilevel_attn_fwd: every query row needs at least one non-zero entry (the reference forces the last two
+ *   columns); zero-filled keys beyond the sequence in a level-1 tail block take part in the softmax with score 0 and
+ *   value 0, exactly like the reference kernel's masked loads (K9:108-119). */
+int blade_multilevel_pyramid(const BladeTensor* k, const BladeTensor* v, void* k2, void* v2, void* k4, void* v4,
+                             void* k8, void* v8, void* stream);
+int blade_multilevel_mask(const float* scores, int64_t B, int64_t H, int64_t nq, int64_t nk,
+                          const uint8_t* rank_level, int32_t force_last, uint8_t* level_mask, int32_t* idx,
+                          int32_t* cnt4, void* stream);
+int blade_level_mask_to_index(const uint8_t* level_mask, int64_t B, int64_t H, int64_t nq, int64_t nk,
+                              int32_t* idx, int32_t* cnt4, void* stream);
+int blade_multilevel_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                              const BladeTensor* k2, const BladeTensor* v2, const BladeTensor* k4,
+                              const BladeTensor* v4, const BladeTensor* k8, const BladeTensor* v8,
+                              const int32_t* idx, const int32_t* cnt4, int64_t idx_stride, BladeTensor* out,
+                              float* lse, const int32_t* dst_row, float softmax_scale, void* workspace,
+                              size_t ws_bytes, void* stream);
+
 /* ---- measurement hook ------------------------------------------------------------------------
  * When set, the library records the given cudaEvent_t pair (passed as void*) on the caller's stream
  * immediately before / after the launches of one stage, so a harness can time a kernel INSIDE a whole-layer

@@ -52,6 +52,7 @@ SYMBOLS = [
     "blade_probe_qk", "blade_probe_pv", "blade_profile_events", "blade_asa_sample_tokens", "blade_asa_scores_sampled",
     "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
     "blade_attn_workspace_bytes", "blade_qk_rms_stat", "blade_qk_rms_stat_peers",
+    "blade_multilevel_pyramid", "blade_multilevel_mask", "blade_level_mask_to_index", "blade_multilevel_attn_fwd",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -77,6 +78,10 @@ def load() -> C.CDLL:
     lib.blade_asa_workspace_bytes.restype = C.c_size_t
     lib.blade_qk_rms_stat.argtypes = [T, T, f32, vp, vp]
     lib.blade_qk_rms_stat_peers.argtypes = [T, T, f32, C.POINTER(vp), i32, i64, i64, vp]
+    lib.blade_multilevel_pyramid.argtypes = [T, T, vp, vp, vp, vp, vp, vp, vp]
+    lib.blade_multilevel_mask.argtypes = [vp, i64, i64, i64, i64, vp, i32, vp, vp, vp, vp]
+    lib.blade_level_mask_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
+    lib.blade_multilevel_attn_fwd.argtypes = [T, T, T, T, T, T, T, T, T, vp, vp, i64, T, vp, vp, f32, vp, C.c_size_t, vp]
     lib.blade_attn_workspace_bytes.argtypes = [i64]
     lib.blade_attn_workspace_bytes.restype = C.c_size_t
     lib.blade_asa_prep.argtypes = [T, T, T, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]

@@ -122,6 +122,9 @@ struct AttnParams {
   // of that peer's [rows, H_total, D] buffer (pointers pre-offset to my first head; out_sh / out_ss describe that layout)
   uint16_t* out_peer[BLADE_MAX_PEERS];
   int out_peer_rows;  // 0 = off
+  // MULTI (multi-level pooled attention, cogvideo_newattn.py N:154-207 + kernel K9:339-692): per (head, query tile) the
+  // number of list entries of level 1, 2, 4, 8; the row's list is sorted by level, then block id
+  const int4* cnt4;
   long long* trace;  // BLADE_TRACE builds: clock64 stamps of CTA 0 (tools/trace_attn.py)
 };
 
@@ -195,6 +198,26 @@ struct Item {
 // Claims run: pair 0 of every head first (those items are up to 6x longer than the rest; started last they were the
 // tail: list scheduling 724 steps vs 613 with them first, mean 608), then the remaining pairs head-major (K/V of
 // ~2 heads stay L2-resident); the last num_solo_pairs claims are issued as two solo tiles each.
+// ---- multi-level tiles: a level-L entry contributes the 128/L mean-pooled keys of its block; L consecutive entries of
+// one level are packed into ONE 128-key tensor-core tile (the softmax is order independent), so a row runs
+// n1 + ceil(n2/2) + ceil(n4/4) + ceil(n8/8) tiles.  Tile j -> level code lc = log2(L), first entry e0, entries ne.
+__device__ __forceinline__ int multi_tiles(const int4 c) {
+  return c.x + ((c.y + 1) >> 1) + ((c.z + 3) >> 2) + ((c.w + 7) >> 3);
+}
+__device__ __forceinline__ void multi_tile(const int4 c, int j, int& lc, int& e0, int& ne) {
+  const int t2 = (c.y + 1) >> 1, t4 = (c.z + 3) >> 2;
+  if (j < c.x) { lc = 0; e0 = j; ne = 1; return; }
+  j -= c.x;
+  if (j < t2) { lc = 1; e0 = c.x + 2 * j; ne = min(2, c.y - 2 * j); return; }
+  j -= t2;
+  if (j < t4) { lc = 2; e0 = c.x + c.y + 4 * j; ne = min(4, c.z - 4 * j); return; }
+  j -= t4;
+  lc = 3; e0 = c.x + c.y + c.z + 8 * j; ne = min(8, c.w - 8 * j);
+}
+struct MultiMaps {
+  CUtensorMap k[3], v[3];  // K / V mean-pooled by 2, 4, 8 (box rows 64, 32, 16)
+};
+
 __device__ __forceinline__ int pair_id_of(const AttnParams& p, int item) {
   const int c = item < p.num_pair_items ? item : p.num_pair_items + ((item - p.num_pair_items) >> 1);
   const int bh_n = p.B * p.H, pph = p.pairs_per_head;
@@ -210,6 +233,12 @@ __device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& 
   if (item < p.num_pair_items) {
     const int pid = pair_id_of(p, item);
     const int bh = pid / p.pairs_per_head, pair = pid % p.pairs_per_head;
+    if (p.cnt4) {  // multi-level: tile counts from the per-level entry counts
+      const int4* row4 = p.cnt4 + static_cast<int64_t>(bh) * p.nq;
+      c0 = multi_tiles(__ldg(row4 + tile_of(p, pair, 0)));
+      if (2 * pair + 1 < p.nq) c1 = multi_tiles(__ldg(row4 + tile_of(p, pair, 1)));
+      return;
+    }
     const int32_t* row = p.cnt + static_cast<int64_t>(bh) * p.nq;
     c0 = __ldg(row + tile_of(p, pair, 0));
     if (2 * pair + 1 < p.nq) c1 = __ldg(row + tile_of(p, pair, 1));
@@ -265,11 +294,10 @@ __device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0,
 }
 
 // ================================================================================================
-template <int D, bool IS_BF16, bool POOLED>
-__global__ void __launch_bounds__(kThreads, 1)
-asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
-                const __grid_constant__ CUtensorMap tmVp, const AttnParams p) {
+template <int D, bool IS_BF16, bool POOLED, bool MULTI>
+__device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                          const CUtensorMap& tmKp, const CUtensorMap& tmVp, const MultiMaps* mm,
+                                          const AttnParams& p) {
   using L = SmemLayout<D>;
   constexpr int kStages = L::kStages;
   constexpr int kTileBytes = L::kTileBytes;
@@ -354,14 +382,20 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int b = bh / p.H, h = bh % p.H;
       int ns[2], nt[2];
       const int32_t* lists[2];
+      int4 c4[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int64_t row = static_cast<int64_t>(bh) * p.nq + it.qb[t];
         ns[t] = it.ns[t];
         nt[t] = it.pt[t] + it.ns[t];
         lists[t] = p.idx + row * p.idx_stride + it.off[t];
+        int n_ent = ns[t];
+        if (MULTI && ns[t] > 0) {
+          c4[t] = __ldg(p.cnt4 + row);
+          n_ent = c4[t].x + c4[t].y + c4[t].z + c4[t].w;  // list entries (>= tiles)
+        }
         // cooperative, coalesced fetch of the block-id list into smem (private to this warp)
-        for (int j = lane; j < ns[t] && j < kMaxListSmem; j += 32)
+        for (int j = lane; j < n_ent && j < kMaxListSmem; j += 32)
           mz->list[t][j] = static_cast<uint16_t>(__ldg(lists[t] + j) & 0x0FFFFFFF);
       }
       __syncwarp();
@@ -383,6 +417,31 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&mz->kv_empty[slot], ph ^ 1);
         const CUtensorMap* map;
         int row;
+        if (MULTI) {
+          // one 128-key tile = L sub-boxes of 128/L pooled rows, one per list entry of this level; a last, partly
+          // filled tile repeats its final entry (finite data; the softmax masks those columns)
+          int lc, e0, ne;
+          multi_tile(c4[t], j, lc, e0, ne);
+          const int rows_per = kBlockN >> lc;
+          map = lc == 0 ? (is_v ? &tmV : &tmK) : (is_v ? &mm->v[lc - 1] : &mm->k[lc - 1]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&mz->kv_full[slot], kTileBytes);
+            for (int gsub = 0; gsub < (1 << lc); ++gsub) {
+              const int e = e0 + (gsub < ne ? gsub : ne - 1);
+              const int kb = e < kMaxListSmem ? static_cast<int>(mz->list[t][e]) : (__ldg(lists[t] + e) & 0x0FFFFFFF);
+#pragma unroll
+              for (int dh = 0; dh < kSub; ++dh)
+                tma_load_4d(sKV + slot * kTileBytes + dh * (kBlockN * 128) + gsub * rows_per * 128, map,
+                            &mz->kv_full[slot], dh * 64, kb * rows_per, h, b, BLADE_KV_HINT);
+            }
+          }
+          __syncwarp();
+          if (++slot == kStages) {
+            slot = 0;
+            ph ^= 1;
+          }
+          return;
+        }
         if (j < it.pt[t]) {
           map = is_v ? &tmVp : &tmKp;
           row = j * kBlockN;
@@ -545,8 +604,16 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int ns = t ? it.ns[1] : it.ns[0];
       const int32_t* my_list =
           p.idx + (static_cast<int64_t>(bh) * p.nq + qb) * p.idx_stride + (t ? it.off[1] : it.off[0]);
-      const int last_kb = ns > 0 ? (__ldg(my_list + ns - 1) & 0x0FFFFFFF) : -1;
-      const int sparse_tail = (last_kb == p.nk - 1) ? seq_tail : kBlockN;
+      int4 c4 = make_int4(0, 0, 0, 0);
+      int last_kb = -1;
+      if (MULTI) {
+        if (ns > 0) c4 = __ldg(p.cnt4 + static_cast<int64_t>(bh) * p.nq + qb);
+      } else {
+        last_kb = ns > 0 ? (__ldg(my_list + ns - 1) & 0x0FFFFFFF) : -1;
+      }
+      // MULTI keeps the zero-filled keys beyond the sequence IN the softmax (score 0, value 0), like the reference
+      // kernel's masked loads (K9:108-119,155-178); only partly filled pooled tiles are masked (per tile, below)
+      const int sparse_tail = (!MULTI && last_kb == p.nk - 1) ? seq_tail : kBlockN;
       float lse2 = 0.f;
       if (wq == 0 && sparse_tail > 0) TRACE(t, 7, g);  // item decoded (both dependent loads done)
 
@@ -563,7 +630,14 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
           tmem_wait_ld();
           if (wq == 0) TRACE(t, 1, g);
-          const int valid = (j == ntile - 1) ? tail_valid : kBlockN;
+          int valid = (j == ntile - 1) ? tail_valid : kBlockN;
+          float bias = 0.f;  // MULTI: + log2(L) on the scaled score (K9: `qk += log(level)`, here in log2 units)
+          if (MULTI) {
+            int lc, e0, ne;
+            multi_tile(c4, j, lc, e0, ne);
+            valid = ne * (kBlockN >> lc);
+            bias = static_cast<float>(lc);
+          }
           float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max chains
           // 64x64 mask granularity (block_size 64): bits (2*rowhalf + colhalf) of the entry's quadrant mask
           unsigned cmask = 3u;
@@ -581,7 +655,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; i += 2)
               mxc[c] = fmaxf(mxc[c], fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sl2;
+          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sl2 + bias;
           if (j == 0) {
             m = mx;
           } else if (m == -INFINITY) {
@@ -609,7 +683,7 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           if (wq == 0) TRACE(t, 2, g);
-          const float neg_m = (m == -INFINITY) ? 0.f : -m;  // all-masked so far: exp2(-inf - 0) = 0, never NaN
+          const float neg_m = ((m == -INFINITY) ? 0.f : -m) + bias;  // all-masked so far: exp2(-inf - 0) = 0, never NaN
           // packed fp32x2 math: x = s * scale - m and the row-sum accumulation take one issue slot per PAIR
           const uint64_t sl2_2 = pack_f32x2(sl2, sl2), negm_2 = pack_f32x2(neg_m, neg_m);
           uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};  // four independent packed sum chains
@@ -814,6 +888,25 @@ asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 11) tmem_dealloc<512>(tmem_base);
 }
 
+template <int D, bool IS_BF16, bool POOLED>
+__global__ void __launch_bounds__(kThreads, 1)
+asa_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
+                const __grid_constant__ CUtensorMap tmVp, const AttnParams p) {
+  attn_body<D, IS_BF16, POOLED, false>(tmQ, tmK, tmV, tmKp, tmVp, nullptr, p);
+}
+
+// Multi-level pooled sparse attention (reference: the Triton `_fwd_kernel`, K9:339-692, behind
+// cogvideo_newattn.py N:210-267): the same pipeline, tiles assembled from the K/V pyramid, `+ log2(level)` in the
+// softmax, one softmax per row (no pooled branch, no merge).
+template <int D, bool IS_BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+asa_multilevel_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ MultiMaps mm,
+                           const AttnParams p) {
+  attn_body<D, IS_BF16, false, true>(tmQ, tmK, tmV, tmK, tmV, &mm, p);
+}
+
 // ================================================================================================
 // bring-up probes: one tile through the same descriptors / TMEM layouts as the main kernel
 // ================================================================================================
@@ -902,6 +995,7 @@ void attn_sched_prezeroed() { g_sched_prezeroed = 1; }
 static thread_local int g_sub64_next = 0;  // set by blade_block_sparse_attn64_fwd / blade_asa_attn64_fwd for one launch
 void attn_next_sub64() { g_sub64_next = 1; }
 
+
 static int device_sm_count() {
   static int n[64] = {0};  // per device: one process may drive several GPUs
   int dev = 0;
@@ -923,7 +1017,8 @@ static float round_host(float x, bool bf16) {
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                 const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
                 int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
-                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream, const BladePeers* peers) {
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream, const BladePeers* peers,
+                const MultiLevelArgs* multi) {
   // one-shot flags set by the callers for exactly this launch: consumed up front, so that an early error return
   // cannot leak them into the next call on this thread
   const bool sched_prezeroed = g_sched_prezeroed != 0;
@@ -934,7 +1029,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
   if (int e = check_tensor16(out, "out")) return e;
-  BLADE_REQUIRE(idx && cnt, BLADE_ERR_ARG, "idx/cnt null");
+  BLADE_REQUIRE(idx && (cnt || multi), BLADE_ERR_ARG, "idx/cnt null");
   const int64_t B = q->shape[0], H = q->shape[1], S = q->shape[2], D = q->shape[3];
   const int64_t Sk = k->shape[2];
   for (int i = 0; i < 4; ++i) {
@@ -1005,7 +1100,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
     static const bool no_split = getenv("BLADE_NO_SPLIT") && atoi(getenv("BLADE_NO_SPLIT")) != 0;
     const int np = (int)(B * H) * p.pairs_per_head, G = device_sm_count();
     int split = 0;
-    if (!no_split) {
+    if (!no_split && !multi) {  // multi-level rows are not split across the two streams
       const int r = np % G;
       if (np < G) split = 2 * np <= G ? np : 0;
       else if (p.sched) split = (G * BLADE_SOLO_NUM / BLADE_SOLO_DEN) < np ? G * BLADE_SOLO_NUM / BLADE_SOLO_DEN : np;
@@ -1049,6 +1144,34 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
   if (p.sched && !sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, sizeof(int), stream));
   StageTimer timer(3, stream);
+  if (multi) {
+    BLADE_REQUIRE(!pooled && !sub64 && multi->cnt4, BLADE_ERR_ARG, "multi-level attention: no pooled branch / block 64");
+    BLADE_REQUIRE((reinterpret_cast<uintptr_t>(multi->cnt4) & 15) == 0, BLADE_ERR_ALIGN, "cnt4 not 16B aligned");
+    MultiMaps mm;
+    for (int l = 0; l < 3; ++l) {
+      const int rows = kBlockN >> (l + 1);
+      for (const BladeTensor* t : {multi->k[l], multi->v[l]}) {
+        if (int e = check_tensor16(t, "pyramid level")) return e;
+        BLADE_REQUIRE(t->shape[0] == B && t->shape[1] == H && t->shape[3] == D && t->shape[2] >= static_cast<int64_t>(nk) * rows &&
+                          t->dtype == q->dtype,
+                      BLADE_ERR_SHAPE, "pyramid level %d: need [B,H,>=%lld,D]", 2 << l, (long long)nk * rows);
+      }
+      if (int e = make_tmap(&mm.k[l], multi->k[l], rows)) return e;
+      if (int e = make_tmap(&mm.v[l], multi->v[l], rows)) return e;
+    }
+    p.cnt4 = reinterpret_cast<const int4*>(multi->cnt4);
+#define LAUNCH_MULTI(DD, BF)                                                                                         \
+  do {                                                                                                               \
+    auto kern = asa_multilevel_attn_kernel<DD, BF>;                                                                  \
+    BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<DD>::kTotal));  \
+    kern<<<grid, kThreads, SmemLayout<DD>::kTotal, stream>>>(tmQ, tmK, tmV, mm, p);                                   \
+  } while (0)
+    if (D == 128) { if (bf) LAUNCH_MULTI(128, true); else LAUNCH_MULTI(128, false); }
+    else          { if (bf) LAUNCH_MULTI(64, true); else LAUNCH_MULTI(64, false); }
+#undef LAUNCH_MULTI
+    BLADE_CUDA_OK(cudaGetLastError());
+    return BLADE_OK;
+  }
 #define LAUNCH_ATTN(DD, BF)                                                                                     \
   do {                                                                                                          \
     auto kern = pooled ? asa_attn_kernel<DD, BF, true> : asa_attn_kernel<DD, BF, false>;                        \
@@ -1089,7 +1212,7 @@ extern "C" int blade_block_sparse_attn_fwd(const BladeTensor* q, const BladeTens
                                            BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
                                            void* workspace, size_t ws_bytes, void* stream) {
   return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
-                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
+                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 // block_size 64 variants: idx entries = (128-key tile id) | (quadrant mask << 28), built by blade_mask64_to_index
@@ -1099,7 +1222,7 @@ extern "C" int blade_block_sparse_attn64_fwd(const BladeTensor* q, const BladeTe
                                              void* workspace, size_t ws_bytes, void* stream) {
   g_sub64_next = 1;
   return launch_attn(q, k, v, idx, cnt, idx_stride, nullptr, nullptr, 0, out, lse, dst_row, softmax_scale, 0, workspace,
-                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
+                     ws_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 extern "C" int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
                                     const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool,
@@ -1109,7 +1232,7 @@ extern "C" int blade_asa_attn64_fwd(const BladeTensor* q, const BladeTensor* k, 
   BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
   g_sub64_next = 1;
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
-                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
@@ -1119,7 +1242,7 @@ extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, co
                                   size_t ws_bytes, void* stream) {
   BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
-                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
+                     exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 #ifdef BLADE_TRACE

@@ -21,15 +21,6 @@ StageEvents* stage_events() {
   return ev;
 }
 
-size_t attn_park_bytes(int64_t D);
-void attn_sched_prezeroed();
-void attn_next_sub64();
-int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
-                const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
-                int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
-                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream,
-                const BladePeers* peers = nullptr);
-
 // ---------------------------------------------------------------------------------------------
 // Generalised Hilbert curve (the algorithm of gilbert3d.py:6-167), iterative, integer 3-vectors.
 // ---------------------------------------------------------------------------------------------

@@ -66,6 +66,22 @@ int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, 
 int rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream,
                   float* const* peer_out = nullptr, int n_peers = 0, int64_t out_rows = 0, int64_t out_row0 = 0);
 
+// ---- attention launch (attn_kernel.cu)
+// multi-level launch: the pooled K/V pyramid (levels 2, 4, 8: [B,H,nk*128/L,D] each) and the per-level entry counts
+struct MultiLevelArgs {
+  const BladeTensor* k[3];
+  const BladeTensor* v[3];
+  const int32_t* cnt4;  // device int32 [B,H,nq,4]: list entries of level 1, 2, 4, 8 (list sorted by level, then block id)
+};
+size_t attn_park_bytes(int64_t D);
+void attn_sched_prezeroed();
+void attn_next_sub64();
+int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
+                const int32_t* cnt, int64_t idx_stride, const BladeTensor* k_pool, const BladeTensor* v_pool,
+                int32_t sample_gap, BladeTensor* out, float* lse, const int32_t* dst_row, float softmax_scale,
+                int exact_merge, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                const BladePeers* peers = nullptr, const MultiLevelArgs* multi = nullptr);
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
