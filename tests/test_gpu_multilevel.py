@@ -175,6 +175,13 @@ def test_layer_matches_reference_module_golden():
     ref = rr.reversed_rearrange(M.multilevel_attention(rr.rearrange(qb).contiguous(), rr.rearrange(kb).contiguous(),
                                                        rr.rearrange(vb).contiguous(), mask))
     _check(out, ref, mean_abs=2e-3, rel=1e-2, mx=2e-2)
-    # and the reference module's own fp32 output: same block scores up to bf16 rounding of the inputs, so a few
-    # blocks may change level -- bounded loosely
-    _check(out, want, mean_abs=1e-2, rel=5e-2)
+    # and the reference module's own fp32 output.  The percentile mask ranks ALL blocks of a row, so the bf16 rounding of
+    # the inputs moves some blocks across a level boundary (different pooling of those keys): the criterion is the one
+    # the reference's own test states for this kernel (mean-abs < 1e-2, test_block_sparse_attention.py:263-271), plus
+    # agreement of the level masks
+    ref32, mask32, _ = M.multilevel_forward(q, k, v, (w, h, d), text, ratios, offs[0], offs[1])
+    assert float((ref32 - want).abs().max()) < 5e-5
+    agree = float((mask32 == mask).float().mean())
+    d = (out.float().cpu() - want).abs()
+    print(f"[multilevel layer vs reference module fp32] mean_abs={float(d.mean()):.2e} level agreement={agree:.3f}")
+    assert float(d.mean()) <= 1e-2 and agree >= 0.7
