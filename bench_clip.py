@@ -24,7 +24,7 @@ if ROOT not in sys.path:
 
 
 def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance=5.0, dense=False, retain=None,
-             data_plane="auto"):
+             data_plane="auto", sampler="generate_new"):
     """One process per GPU; the process group (NCCL) must exist when world > 1.  Returns the result dict on every
     rank (value = max over ranks of the best repetition, seconds)."""
     import torch.distributed as dist
@@ -74,6 +74,13 @@ def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance
     cfg_ranks = None if world == 1 else (branch, 0, P)
     vel = make_velocity_fn(net, prompt, negative, guidance, cfg_ranks)
 
+    if sampler == "unipc":                                       # WanPipeline + UniPC-flow (inference.py:48-52)
+        from video_blade_b200.samplers import sample_unipc_flow
+        generate_new = lambda f, x, steps: sample_unipc_flow(f, x, steps=steps)          # noqa: E731
+    elif sampler == "dpm":                                       # CogVideoXPipeline + DPM "trailing" (inference.py:64-66)
+        from video_blade_b200.samplers import sample_cogvideox_dpm
+        gen_n = torch.Generator(device=dev).manual_seed(3)
+        generate_new = lambda f, x, steps: sample_cogvideox_dpm(f, x, steps=steps, generator=gen_n)   # noqa: E731
     with torch.no_grad():
         generate_new(vel, noise, steps=1)                        # warm-up (cuBLAS plans, workspaces, NCCL)
         torch.cuda.synchronize()
@@ -94,7 +101,8 @@ def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance
     res = {"metric": f"8-step clip seconds ({'CogVideoX-5B' if model == 'cog' else 'Wan2.1-T2V-1.3B'} shape, random init, CFG, synthetic inputs)",
            "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
            "config": {"workload": wname, "layers": layers, "steps": steps, "attention": "dense SDPA" if dense else "ASA",
-                      "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}", "data_plane": plane},
+                      "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}", "data_plane": plane,
+                      "sampler": sampler},
            "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
            "avg_sparsity": None if dense else inner.average_sparsity()}
     del net, vel, out
@@ -113,6 +121,8 @@ def main():
     ap.add_argument("--model", default="wan", choices=["wan", "cog"], help="wan = config 3, cog = config 5")
     ap.add_argument("--retain", type=float, default=None, help="cog density sweep: min = max retain ratio")
     ap.add_argument("--data-plane", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--sampler", default="generate_new", choices=["generate_new", "unipc", "dpm"],
+                    help="generate_new = the trainer's K-step rollout (TW:1402-1443); unipc / dpm = the inference scripts' schedulers")
     a = ap.parse_args()
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -124,7 +134,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     res = run_clip(world, rank, dev, steps=a.steps, layers=a.layers, reps=a.reps, model=a.model, guidance=a.guidance,
-                   dense=a.dense, retain=a.retain, data_plane=a.data_plane)
+                   dense=a.dense, retain=a.retain, data_plane=a.data_plane, sampler=a.sampler)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

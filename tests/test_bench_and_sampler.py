@@ -4,6 +4,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -70,7 +71,7 @@ def test_dit_scaffolds_shapes_and_cfg():
 @pytest.mark.gpu
 def test_bench_json_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3",
-                        "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--no-cpu-baseline", "--no-clip"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -85,6 +86,10 @@ def test_bench_json_contract():
         assert key in line["roofline"]
     assert line["roofline"]["bound"] == "tensor" and 0.2 < line["roofline"]["frac"] < 1.2
     assert line["gpu_launches"] == 3 * 5 and line["value"] > 100
+    mg = line["roofline_maskgen"]                                 # 207.6 MB over the WHOLE mask-gen chain
+    assert mg["bound"] == "hbm" and mg["bytes"] == 207581184 and 0.02 < mg["frac"] < 1.0
+    assert abs(mg["chain_ms"] - sum(line["config"]["stage_ms"][k] for k in ("prep", "scores", "select"))) < 1e-6
+    assert line["hoisted"]["bit_equal_to_per_layer_gather"] is True and "pool" in line["config"]["stage_ms"]
     assert abs(line["config"]["algorithmic_tflop_per_step"] - 1.327) < 0.01
 
 
@@ -123,3 +128,133 @@ def test_algorithmic_flops_match_baseline_formula():
     want = 4 * D * H * float((rows * (cols + n_pool)).sum())
     assert abs(got - want) / want < 1e-12
     assert abs(got / 1e12 - 1.327) < 0.005
+
+
+# ------------------------------------------------------------------ samplers of record
+def test_unipc_flow_schedule_and_first_order_equals_generate_new():
+    """(a) the sigma / timestep schedule of UniPCMultistepScheduler(use_flow_sigmas, flow_shift=3) in closed form;
+    (b) its first-order predictor step is exactly generate_new's update with eta = 1 (TW:1426-1437) for the same pair
+    of sigmas -- both are the exact solution of the flow ODE for a constant x0 prediction."""
+    from video_blade_b200.dit import flow_sigma
+    from video_blade_b200.samplers import UniPCFlowScheduler, flow_sigmas
+    sig = flow_sigmas(8, 3.0)
+    assert sig.shape == (9,) and sig[-1] == 0.0 and all(sig[i] > sig[i + 1] for i in range(8))
+    raw = 1.0 - np.linspace(1.0, 1e-3, 9)[::-1][:-1]
+    assert np.allclose(sig[:-1], 3.0 * raw / (1.0 + 2.0 * raw))
+    # generate_new walks the integer timesteps 999, 874, ...: same schedule up to the rounding of the timestep
+    gn = flow_sigma(torch.tensor([999 - 125 * i for i in range(8)]), 3.0).numpy()
+    assert np.abs(gn - sig[:-1]).max() < 2e-3
+    sch = UniPCFlowScheduler(solver_order=1, use_corrector=False)
+    sch.set_timesteps(8)
+    assert [int(t) for t in sch.timesteps][:3] == [999, 954, 899]          # int(sigma * 1000), like diffusers
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 4, generator=g, dtype=torch.float64)
+    for i in range(8):
+        v = torch.randn(2, 3, 4, generator=g, dtype=torch.float64)
+        s, s2 = sch.sigmas[i], sch.sigmas[i + 1]
+        x0, eps = x - s * v, x + (1 - s) * v                                  # TW:1426, 1431
+        want = (1 - s2) * x0 + s2 * eps                                       # TW:1437 with eta = 1
+        got = sch.step(v, x)
+        assert torch.allclose(got, want, rtol=1e-10, atol=1e-12), i
+        x = got
+    assert torch.allclose(x, x0)                                              # final sigma 0: the sample is the x0 prediction
+
+
+def test_unipc_flow_second_order_beats_first_order_and_is_exact_for_constant_x0():
+    from video_blade_b200.samplers import sample_unipc_flow
+    g = torch.Generator().manual_seed(1)
+    x1 = torch.randn(4, 5, generator=g, dtype=torch.float64)                 # "data"
+    noise = torch.randn(4, 5, generator=g, dtype=torch.float64)
+    # (1) a model whose x0 prediction is constant: every order reproduces x1 exactly
+
+    class ConstX0:
+        def __init__(self, sch_sigmas):
+            self.s, self.i = sch_sigmas, 0
+
+        def __call__(self, x, T):
+            sig = self.s[self.i]
+            self.i += 1
+            return (x - x1) / sig                                             # v such that x - sigma v == x1
+    from video_blade_b200.samplers import UniPCFlowScheduler
+    sch = UniPCFlowScheduler()
+    sch.set_timesteps(8)
+    out = sample_unipc_flow(ConstX0(sch.sigmas), noise, steps=8)
+    assert torch.allclose(out, x1, atol=1e-9)
+
+    # (2) a smooth non-constant x0 prediction x0(x, sigma) = x1 + 0.3 sigma sin(x), integrated from sigma_0 down to the
+    # last non-zero sigma of the 8-step schedule (the final jump to sigma = 0 returns the x0 prediction for every
+    # order).  Reference: the same sigma range in 250 first-order sub-steps per interval.
+    coarse = UniPCFlowScheduler().sigmas.clone()
+
+    def run(sigmas, n_steps, order, corr):
+        sch = UniPCFlowScheduler(solver_order=order, use_corrector=corr)
+        sch.set_timesteps(len(sigmas) - 1)
+        sch.sigmas = sigmas
+        x = noise.clone()
+        for i in range(n_steps):
+            sig = sch.sigmas[i]
+            x0 = x1 + 0.3 * sig * torch.sin(x)
+            x = sch.step((x - x0) / sig, x)
+        return x
+    def refine(kk):
+        return torch.cat([torch.linspace(float(coarse[i]), float(coarse[i + 1]), kk + 1, dtype=torch.float64)[:-1]
+                          for i in range(7)] + [coarse[7:]])
+    ref = run(refine(2000), 7 * 2000, 1, False)
+    err = {(o, kk): float((run(refine(kk), 7 * kk, o, o == 2) - ref).abs().max()) for o in (1, 2) for kk in (1, 2, 4)}
+    assert err[(2, 1)] < 0.5 * err[(1, 1)], err                   # at the 8-step schedule itself
+    assert 1.6 < err[(1, 2)] / err[(1, 4)] < 2.6, err             # first order: halving the step halves the error
+    assert err[(2, 2)] / err[(2, 4)] > 3.0, err                   # predictor-corrector order 2: at least quarters it
+
+
+def test_cogvideox_dpm_trailing_schedule_and_marginals():
+    """(a) "trailing" timesteps 999, 874, ... and the zero-terminal-SNR alphas; (b) every step of the SDE DPM-Solver++
+    maps sqrt(a) x0 + sqrt(1-a) eps to a sample with mean sqrt(a') x0 and variance 1-a' when the x0 prediction is exact
+    -- the property that fixes mult1 / mult2 / mult_noise; (c) the last step returns the x0 prediction."""
+    from video_blade_b200.samplers import CogVideoXDPMScheduler, trailing_timesteps
+    assert trailing_timesteps(8).tolist() == [999, 874, 749, 624, 499, 374, 249, 124]
+    sch = CogVideoXDPMScheduler()
+    ac = sch.alphas_cumprod
+    assert float(ac[-1]) == 0.0 and abs(float(ac[0]) - (1 - 0.00085)) < 1e-12 and bool((ac[:-1] > ac[1:]).all())
+    g = torch.Generator().manual_seed(2)
+    x0 = torch.randn(3, 7, generator=g, dtype=torch.float64)
+    ts = [int(t) for t in sch.timesteps]
+    for i, t in enumerate(ts):
+        a_t = ac[t]
+        a_p = ac[t - 125] if t - 125 >= 0 else torch.tensor(1.0, dtype=torch.float64)
+        eps = torch.randn(3, 7, generator=g, dtype=torch.float64)
+        x = a_t.sqrt() * x0 + (1 - a_t).sqrt() * eps
+        v = a_t.sqrt() * eps - (1 - a_t).sqrt() * x0                          # the exact v-prediction
+        # deterministic skeleton (noise_fn None): mean part
+        prev, pred = sch.step(v, x0 if i else None, t, ts[i - 1] if i else None, x)
+        assert torch.allclose(pred, x0, atol=1e-9)
+        h = sch._lam(a_p) - sch._lam(a_t)
+        m1 = ((1 - a_p) / (1 - a_t)).sqrt() * torch.exp(-h)
+        m_noise = (1 - a_p).sqrt() * (1 - torch.exp(-2 * h)).sqrt()
+        want_mean = a_p.sqrt() * x0 + m1 * (1 - a_t).sqrt() * eps
+        assert torch.allclose(prev, want_mean, atol=1e-9), t
+        assert abs(float(m1 ** 2 * (1 - a_t) + m_noise ** 2 - (1 - a_p))) < 1e-12   # total noise variance = 1 - a'
+    assert torch.allclose(prev, x0, atol=1e-9)
+
+
+def test_clip_samplers_run_on_the_scaffold():
+    """The three samplers drive the same guided-velocity callable (ASA untouched): shapes and finiteness on a tiny DiT."""
+    from video_blade_b200.dit import WanLikeDiT, generate_new, make_velocity_fn
+    from video_blade_b200.modify_wan import WanAttnProcessor2_0
+    from video_blade_b200.samplers import sample_cogvideox_dpm, sample_unipc_flow
+
+    class Dense(torch.nn.Module):
+        def forward(self, q, k, v, **kw):
+            return torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    torch.manual_seed(0)
+    wan = WanLikeDiT(dim=64, heads=2, ffn=128, layers=1, text_dim=32).eval()
+    for b in wan.blocks:
+        b.attn1.inner_attention = Dense()
+        b.attn1.set_processor(WanAttnProcessor2_0())
+    noise = torch.randn(1, 16, 3, 8, 12)
+    vel = make_velocity_fn(wan, torch.randn(1, 7, 32), torch.randn(1, 7, 32), 5.0)
+    with torch.no_grad():
+        a = generate_new(vel, noise, steps=4)
+        b = sample_unipc_flow(vel, noise, steps=4)
+        c = sample_cogvideox_dpm(vel, noise, steps=4, generator=torch.Generator().manual_seed(0))
+    for o in (a, b, c):
+        assert o.shape == noise.shape and torch.isfinite(o).all()
