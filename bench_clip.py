@@ -24,7 +24,7 @@ if ROOT not in sys.path:
 
 
 def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance=5.0, dense=False, retain=None,
-             data_plane="auto", sampler="generate_new"):
+             data_plane="auto", sampler="generate_new", hoist=False):
     """One process per GPU; the process group (NCCL) must exist when world > 1.  Returns the result dict on every
     rank (value = max over ranks of the best repetition, seconds)."""
     import torch.distributed as dist
@@ -63,6 +63,8 @@ def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance
         blocks = net.blocks
         inner = set_adaptive_block_sparse_attn_wanx(net)
         net.set_sequence_parallel(group, data_plane=data_plane)
+        if hoist:
+            net.set_hoisted_permutation(True)
         noise = torch.randn(1, 16, 21, 60, 104, generator=g).to(dev, torch.bfloat16)
         prompt = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
         negative = torch.randn(1, 512, 4096, generator=g).to(dev, torch.bfloat16)
@@ -102,7 +104,7 @@ def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance
            "value": float(t.item()), "unit": "s", "higher_is_better": False, "n_gpus": world,
            "config": {"workload": wname, "layers": layers, "steps": steps, "attention": "dense SDPA" if dense else "ASA",
                       "parallelism": "single (CFG batch 2)" if world == 1 else f"cfg2xulysses{P}", "data_plane": plane,
-                      "sampler": sampler},
+                      "sampler": sampler, "gilbert_permutation": "hoisted to model level" if hoist else "per layer (reference)"},
            "finite": bool(torch.isfinite(out.float()).all()), "all_reps_s": times,
            "avg_sparsity": None if dense else inner.average_sparsity()}
     del net, vel, out
@@ -121,6 +123,7 @@ def main():
     ap.add_argument("--model", default="wan", choices=["wan", "cog"], help="wan = config 3, cog = config 5")
     ap.add_argument("--retain", type=float, default=None, help="cog density sweep: min = max retain ratio")
     ap.add_argument("--data-plane", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--hoist", action="store_true", help="Wan: permute tokens into curve order once per forward (SURVEY 7.3)")
     ap.add_argument("--sampler", default="generate_new", choices=["generate_new", "unipc", "dpm"],
                     help="generate_new = the trainer's K-step rollout (TW:1402-1443); unipc / dpm = the inference scripts' schedulers")
     a = ap.parse_args()
@@ -134,7 +137,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     res = run_clip(world, rank, dev, steps=a.steps, layers=a.layers, reps=a.reps, model=a.model, guidance=a.guidance,
-                   dense=a.dense, retain=a.retain, data_plane=a.data_plane, sampler=a.sampler)
+                   dense=a.dense, retain=a.retain, data_plane=a.data_plane, sampler=a.sampler, hoist=a.hoist)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

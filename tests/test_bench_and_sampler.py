@@ -258,3 +258,49 @@ def test_clip_samplers_run_on_the_scaffold():
         c = sample_cogvideox_dpm(vel, noise, steps=4, generator=torch.Generator().manual_seed(0))
     for o in (a, b, c):
         assert o.shape == noise.shape and torch.isfinite(o).all()
+
+
+def test_hoisted_gilbert_permutation_is_equivalent_on_the_scaffold():
+    """permuting the tokens (and their rotary table) into curve order once per forward and running the
+    attention without its per-layer gather gives the same model output -- every other op is token-wise."""
+    from video_blade_b200 import wanx_blocksparseattn as W
+    from video_blade_b200.dit import WanLikeDiT
+    from video_blade_b200.modify_wan import WanAttnProcessor2_0
+
+    class CurveLocalInner(torch.nn.Module):
+        """Stand-in for ASA on CPU with the property that matters here: it is NOT permutation equivariant -- like ASA it
+        gathers into curve order (when use_rearrange), attends within blocks of 16 consecutive curve positions, and
+        scatters back."""
+        use_rearrange = True
+
+        def forward(self, q, k, v, **kw):
+            from video_blade_b200.asa import token_order
+            S = q.shape[2]
+            order = torch.from_numpy(token_order(W._knobs())).long()
+            if self.use_rearrange:
+                q, k, v = q[:, :, order], k[:, :, order], v[:, :, order]
+            o = torch.cat([torch.nn.functional.scaled_dot_product_attention(q[:, :, i:i + 16], k[:, :, i:i + 16],
+                                                                             v[:, :, i:i + 16]) for i in range(0, S, 16)], 2)
+            if self.use_rearrange:
+                back = torch.empty_like(o)
+                back[:, :, order] = o
+                o = back
+            return o
+    old = (W.width, W.height, W.depth)
+    W.width, W.height, W.depth = 6, 4, 3                                       # 72 tokens: lat [1,16,3,8,12], patch (1,2,2)
+    try:
+        torch.manual_seed(0)
+        net = WanLikeDiT(dim=64, heads=2, ffn=128, layers=2, text_dim=32).eval()
+        inner = CurveLocalInner()
+        for b in net.blocks:
+            b.attn1.inner_attention = inner
+            b.attn1.set_processor(WanAttnProcessor2_0())
+        lat, ctx, t = torch.randn(1, 16, 3, 8, 12), torch.randn(1, 7, 32), torch.tensor([500])
+        with torch.no_grad():
+            ref = net(lat, t, ctx)
+            net.set_hoisted_permutation(True)
+            assert inner.use_rearrange is False
+            got = net(lat, t, ctx)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), float((got - ref).abs().max())
+    finally:
+        W.width, W.height, W.depth = old

@@ -119,8 +119,27 @@ def _dtype_code(t) -> int:
     return {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32, torch.int32: I32, torch.uint8: U8}[t.dtype]
 
 
+class TensorLayout:
+    """A [B,H,S,D] layout descriptor without storage behind all of it: base pointer, shape, element strides, dtype.
+    Used where the rows of a logical tensor live in several GPUs' memories (Ulysses peer pull / push): the kernels take
+    the per-peer base pointers from BladePeers and only the geometry from here."""
+
+    def __init__(self, ptr: int, shape, stride, dtype, device):
+        self._ptr, self.shape, self._stride, self.dtype, self.device = int(ptr), tuple(shape), tuple(stride), dtype, device
+        self.is_cuda = True
+
+    def dim(self):
+        return len(self.shape)
+
+    def stride(self, i=None):
+        return self._stride if i is None else self._stride[i]
+
+    def data_ptr(self):
+        return self._ptr
+
+
 def tensor_desc(t) -> BladeTensor:
-    """[B,H,S,D] torch tensor (any strides, last dim contiguous) -> BladeTensor."""
+    """[B,H,S,D] torch tensor (any strides, last dim contiguous) or TensorLayout -> BladeTensor."""
     assert t.dim() == 4, "expected [B,H,S,D]"
     d = BladeTensor()
     d.ptr = t.data_ptr()

@@ -167,7 +167,7 @@ class AsaEngine:
     @staticmethod
     def _require_cuda(*ts):
         for t in ts:
-            if t is not None and not t.is_cuda:
+            if t is not None and not getattr(t, "is_cuda", False):
                 raise RuntimeError("video_blade_b200 runs on CUDA tensors only (no CPU fallback)")
 
     # ---- stage entry points (same roles as the reference helpers) ------------------------

@@ -232,6 +232,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   const bool norm_on = cfg->qk_norm != nullptr && cfg->qk_norm->kind != 0;
   const bool pull = cfg->peers != nullptr && cfg->peers->q[0] != nullptr;  // q/k/v rows live in the peers' memory
   const bool rearr = src_row != nullptr || cfg->rope_cos_sin != nullptr || norm_on || pull;  // these need the output copies
+  const bool v_copy = src_row != nullptr || pull;  // rope / norm rewrite q and k only: v is then read in place
   PrepNorm pn{};
   if (norm_on) {
     pn.kind = cfg->qk_norm->kind;
@@ -255,7 +256,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   const bool need_means = scores_in == nullptr && !sampled;
   // gather / rotate / block means on the caller's stream ...
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
-                        rearr ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
+                        v_copy ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
                         stream, norm_on ? &pn : nullptr, cfg->token_row, cfg->peers))
     return e;
@@ -272,7 +273,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   }
   auto run_pool = [&]() -> int {
     return prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
-                     rearr ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool, cfg->block_size,
+                     v_copy ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool, cfg->block_size,
                      cfg->sample_gap, nullptr, 0, 2, pstream);
   };
   if (np && fork_mode != 1)
@@ -282,10 +283,14 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     const int64_t cs[4] = {H * S * D, S * D, D, 1};
     qr.ptr = ws + w.q_r;
     kr.ptr = ws + w.k_r;
-    vr.ptr = ws + w.v_r;
-    for (int i = 0; i < 4; ++i) qr.stride[i] = kr.stride[i] = vr.stride[i] = cs[i];
+    for (int i = 0; i < 4; ++i) qr.stride[i] = kr.stride[i] = cs[i];
+    if (v_copy) {
+      vr.ptr = ws + w.v_r;
+      for (int i = 0; i < 4; ++i) vr.stride[i] = cs[i];
+    }
   }
   const float* sc = scores_in;
+  bool fused_select = false;
   if (sampled) {
     // the reference's estimator (efficient_attn_with_pooling, W:62-87 -> P:201-253) on the gathered / rotated /
     // normalised q and k: sample num_keep rows per block, then the tcgen05 score kernel
@@ -295,8 +300,20 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     if (int e = blade_asa_scores_sampled(ws + w.q_s, ws + w.k_s, scores, B, H, nb, D, q->dtype, mstream)) return e;
     sc = scores;
   } else if (!sc) {
-    if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, mstream)) return e;
-    sc = scores;
+    // mean-pool estimator: block-score GEMM + softmax + selection in ONE launch (the fp32 score map only goes to memory
+    // when the caller asked for it); shapes the fused kernel does not cover take the two-kernel path below
+    static const bool no_fuse = getenv("BLADE_NO_FUSED_SELECT") && atoi(getenv("BLADE_NO_FUSED_SELECT")) != 0;  // A/B knob
+    int rc = -1;
+    if (!no_fuse)
+      rc = score_select_impl(q_mean, k_mean, scores_out, B, H, nb, D, cfg, blk64 ? reinterpret_cast<int32_t*>(ws + w.idx) : idx,
+                             cnt, blk64 ? (mask_out ? mask_out : ws + w.mask64) : mask_out, mstream, false);
+    if (rc > 0) return rc;
+    if (rc == 0) {
+      fused_select = true;
+    } else {
+      if (int e = blade_asa_scores_meanpool(q_mean, k_mean, scores, B, H, nb, D, mstream)) return e;
+      sc = scores;
+    }
   } else if (scores_out) {
     BLADE_CUDA_OK(cudaMemcpyAsync(scores_out, scores_in, B * H * nb * nb * 4, cudaMemcpyDeviceToDevice, mstream));
   }
@@ -311,12 +328,13 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     int32_t* i64 = reinterpret_cast<int32_t*>(ws + w.idx);
     int32_t* i128 = idx_out ? idx_out : reinterpret_cast<int32_t*>(ws + w.idx128);
     int32_t* c128 = reinterpret_cast<int32_t*>(ws + w.cnt128);
-    if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, i64, cnt, m64, nullptr, mstream)) return e;
+    if (!fused_select)
+      if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, i64, cnt, m64, nullptr, mstream)) return e;
     if (int e = blade_mask64_to_index(m64, B, H, nb, nb, i128, c128, mstream)) return e;
     attn_idx = i128;
     attn_cnt = c128;
     attn_stride = ceil_div(nb, 2);
-  } else {
+  } else if (!fused_select) {
     if (int e = blade_asa_select(sc, B, H, nb, nb, cfg, nullptr, nullptr, idx, cnt, mask_out, nullptr, mstream)) return e;
   }
   if (np && fork_mode == 1)

@@ -63,6 +63,9 @@ int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, 
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
               int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream,
               const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr, const BladePeers* peers = nullptr);
+int score_select_impl(const float* q_mean, const float* k_mean, float* scores_opt, int64_t B, int64_t H, int64_t nb,
+                      int64_t D, const BladeAsaConfig* cfg, int32_t* idx, int32_t* cnt, uint8_t* mask_opt,
+                      cudaStream_t stream, bool pdl);
 int rms_stat_impl(const BladeTensor* q, const BladeTensor* k, float eps, float* out, cudaStream_t stream,
                   float* const* peer_out = nullptr, int n_peers = 0, int64_t out_rows = 0, int64_t out_row0 = 0);
 

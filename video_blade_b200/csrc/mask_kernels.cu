@@ -160,7 +160,7 @@ struct PeerSrc {
   int rows;  // 0 = off
 };
 
-template <int D, bool IS_BF16, bool COPY, bool ROPE, bool NORM>
+template <int D, bool IS_BF16, bool COPY, bool ROPE, bool NORM, bool PEER>
 __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
                                                          const uint16_t* __restrict__ v, Strides3 sq, Strides3 sk,
                                                          Strides3 sv, const int32_t* __restrict__ src_row,
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
         srcs[u] = ((ROPE || NORM) && tok_row) ? __ldg(tok_row + rc) : sr;  // token index (rotary table / norm statistic)
         if (p < passes) {
           const uint16_t* rowp;
-          if (peer.rows) {  // uniform: pull the row over NVLink from the peer that owns token sr
+          if (PEER) {  // compile-time: pull the row over NVLink from the peer that owns token sr
             const int pp = sr / peer.rows;
             rowp = peer.base[t][pp] + h * st.h + static_cast<int64_t>(sr - pp * peer.rows) * st.s;
           } else {
@@ -402,10 +402,11 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreRows = 16;
 constexpr int kScoreChunk = 64;
+// Body shared by score_meanpool_kernel and the fused score + selection kernel: leaves the CTA's 16 softmax rows in
+// shared memory (srow, [16][nb]) and, if `scores` is given, writes them to global memory.
 template <int D>
-__global__ void __launch_bounds__(256, 3) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
-                                                             float* __restrict__ scores, int nb, float scale) {
-  extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void score_rows_16(const float* __restrict__ qm, const float* __restrict__ km,
+                                              float* __restrict__ scores, int nb, float scale, float* sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int DP = D + 4;
   constexpr int d4n = D / 4;
@@ -489,9 +490,63 @@ __global__ void __launch_bounds__(256, 3) score_meanpool_kernel(const float* __r
 #pragma unroll
     for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     const float inv = 1.0f / sum;
-    float* out = scores + (bh * nb + i) * nb;
-    for (int j = lane; j < nb; j += 32) out[j] = row[j] * inv;
+    float* out = scores ? scores + (bh * nb + i) * nb : nullptr;
+    for (int j = lane; j < nb; j += 32) {
+      const float v = row[j] * inv;
+      row[j] = v;
+      if (out) out[j] = v;
+    }
   }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 3) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
+                                                             float* __restrict__ scores, int nb, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  score_rows_16<D>(qm, km, scores, nb, scale, sm);
+}
+
+template <int E>
+__device__ __forceinline__ int select_row_bitonic(const float* src, int nk, int qi, int nq, int lo, int hi, float thr,
+                                                  int force_last, int rounding, double* sorted, int* flag,
+                                                  int32_t* irow, uint8_t* mrow, int32_t* kcut_out, int lane);
+
+// Fused mask generation back end (north-star kernel (a), second half): block-score GEMM on the means + row softmax +
+// energy-threshold selection + index list, one launch; the fp32 score map only goes to memory when the caller asks for
+// it.  Same arithmetic, bit for bit, as score_meanpool_kernel followed by select_bitonic_kernel<E> (the selection reads
+// the rows from shared memory instead of global).  dynamic smem: the score part + 8 warps * (N doubles + N ints).
+template <int D, int E>
+__global__ void __launch_bounds__(256, 2) score_select_kernel(const float* __restrict__ qm, const float* __restrict__ km,
+                                                           float* __restrict__ scores_opt, int nb, float scale, int lo,
+                                                           int hi, float thr, int force_last, int rounding,
+                                                           int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
+                                                           uint8_t* __restrict__ mask,
+                                                           unsigned long long* __restrict__ sel_acc) {
+  constexpr int N = 32 * E;
+  extern __shared__ __align__(16) float sm[];
+  // programmatic dependent launch: everything above the first global read may overlap the producer's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  score_rows_16<D>(qm, km, scores_opt, nb, scale, sm);
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* srow = sm + kScoreRows * D;
+  const size_t score_floats = static_cast<size_t>(kScoreRows) * (D + nb) + kScoreChunk * (D + 4);
+  double* sorted = reinterpret_cast<double*>(sm + ((score_floats + 1) & ~size_t(1))) + warp * 2 * N;
+  int* flag = reinterpret_cast<int*>(sorted + N);
+  const int64_t bh = blockIdx.y;
+  int total = 0;
+  for (int rr = 0; rr < kScoreRows / 8; ++rr) {
+    const int r = warp * (kScoreRows / 8) + rr;
+    const int qi = blockIdx.x * kScoreRows + r;
+    if (qi >= nb) break;
+    const int64_t row = bh * nb + qi;
+    const int base = select_row_bitonic<E>(srow + r * nb, nb, qi, nb, lo, hi, thr, force_last, rounding, sorted, flag,
+                                           idx + row * nb, mask ? mask + row * nb : nullptr, nullptr, lane);
+    if (lane == 0) cnt[row] = base;
+    total += base;
+  }
+  if (sel_acc && lane == 0 && total) atomicAdd(sel_acc, static_cast<unsigned long long>(total));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -588,32 +643,13 @@ __global__ void __launch_bounds__(256) select_rank_kernel(const float* __restric
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// select (nk <= 256): one warp per score row, E = elements per lane (nk <= 32*E).  The row is sorted by a
-// bitonic network held in registers (position p = lane*E + r; partners with j < E are in-lane, the others one
-// __shfl_xor away) under the total order (value desc, index asc) -- the same order as torch.sort(stable=True),
-// unique keys so the network's instability does not matter.  Then: fp64 sequential prefix sums by lane 0
-// (bit-exact with torch's CPU cumsum), clamp, flag scatter, ballot compaction to the ascending index list.
-// dynamic smem: 8 warps * 2 * 32*E doubles (sorted values as fp64 + int flags).
-// ------------------------------------------------------------------------------------------------
+// One score row through the selection: `src` = the row's nk fp32 scores (global or shared memory), sorted / flag = this
+// warp's scratch (N doubles + N ints).  Returns the number of selected blocks (all lanes).
 template <int E>
-__global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __restrict__ scores, int64_t total_rows, int nq,
-                                                             int nk, int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
-                                                             const int32_t* __restrict__ hi_bh, float thr, int force_last,
-                                                             int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
-                                                             uint8_t* __restrict__ mask, int32_t* __restrict__ kcut,
-                                                             int rounding, unsigned long long* __restrict__ sel_acc) {
+__device__ __forceinline__ int select_row_bitonic(const float* src, int nk, int qi, int nq, int lo, int hi, float thr,
+                                                  int force_last, int rounding, double* sorted, int* flag,
+                                                  int32_t* irow, uint8_t* mrow, int32_t* kcut_out, int lane) {
   constexpr int N = 32 * E;
-  extern __shared__ __align__(16) float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sorted = reinterpret_cast<double*>(sm) + warp * 2 * N;   // sorted values, widened in parallel
-  int* flag = reinterpret_cast<int*>(sorted + N);                 // flag[original index] = selected
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
-  if (row >= total_rows) return;
-  const int qi = static_cast<int>(row % nq);
-  const int64_t bh = row / nq;
-  const float* src = scores + row * nk;
-
   // One 64-bit key per element: high word = the value's bits mapped to an order-preserving unsigned, low word =
   // ~index.  "a before b" (value desc, index asc) is then a single unsigned compare ka > kb: 2 ISETP + 2 SEL per
   // compare-exchange instead of three compares, predicate logic and two selects (the ALU pipe bounds this kernel).
@@ -622,7 +658,7 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int p = lane * E + r;
-    const float x = p < nk ? __ldg(src + p) + 0.0f : -INFINITY;  // padding sorts behind every real entry
+    const float x = p < nk ? src[p] + 0.0f : -INFINITY;  // padding sorts behind every real entry
     const uint32_t b = __float_as_uint(x);
     const uint32_t mono = b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
     key[r] = (static_cast<uint64_t>(mono) << 32) | static_cast<uint32_t>(~p);
@@ -669,23 +705,18 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
     flag[lane * E + r] = 0;
   }
   __syncwarp();
-
-  const int lo = lo_bh ? lo_bh[bh] : lo_s;
-  const int hi = hi_bh ? hi_bh[bh] : hi_s;
   int kfirst = nk;
   if (lane == 0) kfirst = energy_cut(sorted, nk, hi < nk ? hi : nk /* beyond `hi` the clamp decides */, thr, rounding);
   kfirst = __shfl_sync(0xffffffffu, kfirst, 0);
   int kc = kfirst < lo ? lo : kfirst;
   kc = kc > hi ? hi : kc;
-  if (kcut && lane == 0) kcut[row] = kc;
+  if (kcut_out && lane == 0) *kcut_out = kc;
 #pragma unroll
   for (int r = 0; r < E; ++r)
     if (lane * E + r < kc && id[r] < nk) flag[id[r]] = 1;    // sorted position < cut  ->  keep that block
   __syncwarp();
 
   const bool full_row = force_last > 0 && qi >= nq - force_last;
-  int32_t* irow = idx + row * nk;
-  uint8_t* mrow = mask ? mask + row * nk : nullptr;
   int base = 0;
 #pragma unroll
   for (int sblk = 0; sblk < E; ++sblk) {
@@ -697,6 +728,39 @@ __global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __rest
     base += __popc(bal);
   }
   for (int j = base + lane; j < nk; j += 32) irow[j] = -1;
+  __syncwarp();
+  return base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// select (nk <= 256): one warp per score row, E = elements per lane (nk <= 32*E).  The row is sorted by a
+// bitonic network held in registers (position p = lane*E + r; partners with j < E are in-lane, the others one
+// __shfl_xor away) under the total order (value desc, index asc) -- the same order as torch.sort(stable=True),
+// unique keys so the network's instability does not matter.  Then: fp64 sequential prefix sums by lane 0
+// (bit-exact with torch's CPU cumsum), clamp, flag scatter, ballot compaction to the ascending index list.
+// dynamic smem: 8 warps * 2 * 32*E doubles (sorted values as fp64 + int flags).
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256) select_bitonic_kernel(const float* __restrict__ scores, int64_t total_rows, int nq,
+                                                             int nk, int lo_s, int hi_s, const int32_t* __restrict__ lo_bh,
+                                                             const int32_t* __restrict__ hi_bh, float thr, int force_last,
+                                                             int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
+                                                             uint8_t* __restrict__ mask, int32_t* __restrict__ kcut,
+                                                             int rounding, unsigned long long* __restrict__ sel_acc) {
+  constexpr int N = 32 * E;
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sorted = reinterpret_cast<double*>(sm) + warp * 2 * N;   // sorted values, widened in parallel
+  int* flag = reinterpret_cast<int*>(sorted + N);                 // flag[original index] = selected
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= total_rows) return;
+  const int qi = static_cast<int>(row % nq);
+  const int64_t bh = row / nq;
+  const int lo = lo_bh ? lo_bh[bh] : lo_s;
+  const int hi = hi_bh ? hi_bh[bh] : hi_s;
+  const int base = select_row_bitonic<E>(scores + row * nk, nk, qi, nq, lo, hi, thr, force_last, rounding, sorted, flag,
+                                         idx + row * nk, mask ? mask + row * nk : nullptr, kcut ? kcut + row : nullptr,
+                                         lane);
   if (lane == 0) {
     cnt[row] = base;
     if (sel_acc) atomicAdd(sel_acc, static_cast<unsigned long long>(base));
@@ -845,7 +909,9 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   BLADE_REQUIRE(block_size == 64 || block_size == 128, BLADE_ERR_ARG, "block_size %d not in {64,128}", block_size);
   BLADE_REQUIRE(S >= 1 && B >= 1 && H >= 1 && H <= 65535 && B <= 65535, BLADE_ERR_SHAPE, "bad B/H/S");
   const bool copy = q_r || k_r || v_r;
-  BLADE_REQUIRE(!copy || (q_r && k_r && v_r), BLADE_ERR_ARG, "q_r/k_r/v_r must be all set or all NULL");
+  // v is only rewritten when rows move (gather / peer pull); rope and norm touch q and k alone, so v_r may stay NULL then
+  BLADE_REQUIRE(!copy || (q_r && k_r && (v_r || (!src_row && !(peers && peers->q[0])))), BLADE_ERR_ARG,
+                "q_r/k_r must both be set, and v_r too when src_row / peers move rows");
   PeerSrc psrc{};
   if (peers && peers->q[0]) {
     BLADE_REQUIRE(peers->n_peers >= 1 && peers->n_peers <= BLADE_MAX_PEERS && peers->my_peer >= 0 &&
@@ -904,11 +970,15 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   }
   if ((parts & 1) && (q_mean || k_mean || copy)) {
     dim3 grid(nb, static_cast<unsigned>(H), static_cast<unsigned>(B));
-#define LAUNCH_PREP(DD, BF, CP, RP, NM)                                                                               \
-  prep_block_kernel<DD, BF, CP, RP, NM><<<grid, 256, 0, stream>>>(                                                    \
+#define LAUNCH_PREP_P(DD, BF, CP, RP, NM, PE)                                                                         \
+  prep_block_kernel<DD, BF, CP, RP, NM, PE><<<grid, 256, 0, stream>>>(                                                \
       qp, kp, vp, sq, sk, sv, src_row, static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r),                      \
       static_cast<uint16_t*>(v_r), q_mean, k_mean, static_cast<int>(S), static_cast<int>(H), nb, block_size,          \
       rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps, psrc)
+#define LAUNCH_PREP(DD, BF, CP, RP, NM)                                                                               \
+  do {                                                                                                                \
+    if (CP && psrc.rows) LAUNCH_PREP_P(DD, BF, CP, RP, NM, (CP)); else LAUNCH_PREP_P(DD, BF, CP, RP, NM, false);      \
+  } while (0)
 #define LAUNCH_PREP_B(DD, CP, RP, NM)                                                                                 \
   do {                                                                                                                \
     if (bf) LAUNCH_PREP(DD, true, CP, RP, NM); else LAUNCH_PREP(DD, false, CP, RP, NM);                               \
@@ -925,16 +995,17 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
 #undef LAUNCH_PREP_D
 #undef LAUNCH_PREP_B
 #undef LAUNCH_PREP
+#undef LAUNCH_PREP_P
     BLADE_CUDA_OK(cudaGetLastError());
   }
   if ((parts & 2) && sample_gap > 0 && k_pool && v_pool) {
     const int np = static_cast<int>(ceil_div(S, sample_gap));
     // read the curve-ordered copies when they exist (contiguous, no gather), else the sources
     const uint16_t* ks = copy ? static_cast<const uint16_t*>(k_r) : kp;
-    const uint16_t* vs = copy ? static_cast<const uint16_t*>(v_r) : vp;
+    const uint16_t* vs = v_r ? static_cast<const uint16_t*>(v_r) : vp;
     Strides3 ck{H * S * D, S * D, D};
-    Strides3 pk = copy ? ck : sk, pv = copy ? ck : sv;
-    const int32_t* sr = copy ? nullptr : src_row;
+    Strides3 pk = copy ? ck : sk, pv = v_r ? ck : sv;
+    const int32_t* sr = copy ? nullptr : src_row;   // (no v copy implies no src_row: both tensors are read in place)
     dim3 grid(static_cast<unsigned>(ceil_div(np, 8)), static_cast<unsigned>(H), static_cast<unsigned>(B));
 #define LAUNCH_POOL(DD, BF)                                                                                      \
   pool_kernel<DD, BF><<<grid, 256, 0, stream>>>(ks, vs, pk, pv, sr, static_cast<uint16_t*>(k_pool),             \
@@ -963,6 +1034,52 @@ extern "C" int blade_asa_scores_meanpool(const float* q_mean, const float* k_mea
     BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, 256, smem, stream>>>(q_mean, k_mean, scores, (int)nb, scale);
   BLADE_CUDA_OK(cudaGetLastError());
+  return BLADE_OK;
+}
+
+// fused scores + selection (nb <= 256); returns BLADE_OK, or -1 when the shape needs the two-kernel path
+int blade::score_select_impl(const float* q_mean, const float* k_mean, float* scores_opt, int64_t B, int64_t H, int64_t nb,
+                             int64_t D, const BladeAsaConfig* cfg, int32_t* idx, int32_t* cnt, uint8_t* mask_opt,
+                             cudaStream_t stream, bool pdl) {
+  if (nb > 256 || (D != 64 && D != 128)) return -1;
+  const int E = nb <= 32 ? 1 : (nb <= 64 ? 2 : (nb <= 128 ? 4 : 8));
+  const size_t score_floats = static_cast<size_t>(kScoreRows) * (D + nb) + kScoreChunk * (D + 4);
+  const size_t smem = ((score_floats + 1) & ~size_t(1)) * sizeof(float) + 8 * (2 * 32 * E) * sizeof(double);
+  if (smem > 200 * 1024) return -1;
+  BLADE_REQUIRE(cfg->min_retain >= 1 && cfg->max_retain >= 1, BLADE_ERR_ARG, "retain bounds must be >= 1");
+  BLADE_REQUIRE(cfg->select_rounding >= 0 && cfg->select_rounding <= 2, BLADE_ERR_ARG, "select_rounding %d not in {0,1,2}",
+                cfg->select_rounding);
+  StageTimer t1(1, stream);   // the fused launch is reported as stage 1 (scores); stage 2 (select) collapses to ~0
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(static_cast<unsigned>(ceil_div(nb, kScoreRows)), static_cast<unsigned>(B * H));
+  lc.blockDim = dim3(256);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl ? 1 : 0;
+  const int nbi = static_cast<int>(nb);
+#define LAUNCH_FUSED(DD, EE)                                                                                          \
+  do {                                                                                                                \
+    auto kern = score_select_kernel<DD, EE>;                                                                          \
+    if (smem > 48 * 1024)                                                                                             \
+      BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    BLADE_CUDA_OK(cudaLaunchKernelEx(&lc, kern, q_mean, k_mean, scores_opt, nbi, scale, (int)cfg->min_retain,         \
+                                     (int)cfg->max_retain, cfg->energy_threshold, (int)cfg->force_last,               \
+                                     (int)cfg->select_rounding, idx, cnt, mask_opt, cfg->selected_acc));              \
+  } while (0)
+#define LAUNCH_FUSED_D(DD)                                                                                            \
+  do {                                                                                                                \
+    if (E == 1) LAUNCH_FUSED(DD, 1); else if (E == 2) LAUNCH_FUSED(DD, 2); else if (E == 4) LAUNCH_FUSED(DD, 4);      \
+    else LAUNCH_FUSED(DD, 8);                                                                                         \
+  } while (0)
+  if (D == 128) LAUNCH_FUSED_D(128); else LAUNCH_FUSED_D(64);
+#undef LAUNCH_FUSED_D
+#undef LAUNCH_FUSED
+  { StageTimer t2(2, stream); }
   return BLADE_OK;
 }
 

@@ -234,6 +234,30 @@ class WanLikeDiT(nn.Module):
         self.head_table = nn.Parameter(torch.randn(1, 2, dim) / dim ** 0.5)
         self.group: Optional[UlyssesGroup] = None
         self._rope = {}
+        self.hoist = False
+        self._order = {}
+
+    def set_hoisted_permutation(self, on: bool = True):
+        """Model-level hoist of the Gilbert permutation: every token-wise op is permutation equivariant, so
+        the tokens (and their rotary table) are put into curve order ONCE per forward, the shared ASA module runs with
+        use_rearrange = False (no per-layer gather of q, k, v, no inverse permutation of the output), and the sequence
+        is put back before unpatchify.  The reference permutes inside every layer (W:142-159); the drop-in default
+        keeps that.  With sequence parallelism the ranks then own contiguous curve segments."""
+        self.hoist = bool(on)
+        for blk in self.blocks:
+            blk.attn1.inner_attention.use_rearrange = not self.hoist
+
+    def _curve_order(self, S, device):
+        key = (S, str(device))
+        if key not in self._order:
+            from . import wanx_blocksparseattn as W
+            from .asa import token_order
+            order = torch.from_numpy(token_order(W._knobs())).long().to(device)
+            assert order.numel() == S, (order.numel(), S)
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(S, device=device)
+            self._order[key] = (order, inv)
+        return self._order[key]
 
     def set_sequence_parallel(self, group: Optional[UlyssesGroup], data_plane: str = "auto"):
         """data_plane: "p2p" = NVLink peer-memory pull/push inside the layer's kernels (UlyssesPeerPlane, needs
@@ -297,6 +321,9 @@ class WanLikeDiT(nn.Module):
             self._rope[key] = rope_freqs(*grid, self.dim // self.heads, device=x.device)
         rope = self._rope[key]
         g = self.group
+        if self.hoist:                                         # curve order once per forward, not once per layer
+            order, inv_order = self._curve_order(S, x.device)
+            x, rope = x[:, order], rope[:, :, order]
         if g is not None and g.P > 1:                          # keep my S/P token shard
             sl = slice(g.rank_in_group * (S // g.P), (g.rank_in_group + 1) * (S // g.P))
             self._ensure_plane(S // g.P, x.device, next(self.parameters()).dtype)
@@ -317,6 +344,8 @@ class WanLikeDiT(nn.Module):
             parts = [torch.empty_like(x) for _ in range(g.P)]
             dist.all_gather(parts, x.contiguous(), group=g.group)
             x = torch.cat(parts, dim=1)
+        if self.hoist:
+            x = x[:, inv_order]
         return self.unpatchify(x, grid, self.in_ch)
 
 

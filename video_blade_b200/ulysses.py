@@ -136,11 +136,14 @@ class UlyssesPeerPlane:
         self.hdl.barrier(channel=0)
 
     def views(self):
-        """[1, Hl, S, D] layout descriptors of q/k/v for the engine (rows are pulled from the peers)."""
+        """[1, Hl, S, D] layout descriptors of q/k/v for the engine: geometry only -- the S rows live in the P peers'
+        buffers (Sl each) and are pulled from there, so no local tensor can back them."""
+        from ._lib import TensorLayout
         Hl, S, D, H = self.Hl, self.S, self.D, self.H
-        base = self.g.rank_in_group * Hl * D
-        return tuple(self.qkv[j].as_strided((1, Hl, S, D), (0, D, H * D, 1), self.qkv[j].storage_offset() + base)
-                     for j in range(3))
+        esz = self.qkv.element_size()
+        base = self.g.rank_in_group * Hl * D * esz
+        return tuple(TensorLayout(self.qkv[j].data_ptr() + base, (1, Hl, S, D), (S * H * D, D, H * D, 1), self.qkv.dtype,
+                                  self.qkv.device) for j in range(3))
 
     def push_rms_stat(self, eng, eps: float):
         """rstd of my tokens (q and k, all heads: MW:99-102) stored into every peer's table."""
