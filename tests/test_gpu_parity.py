@@ -696,3 +696,44 @@ def test_sampled_max_one_call_with_fused_rope_and_offsets():
     assert torch.equal(dbg["mask"].cpu(), ref.mask)
     rr = O.GilbertRearranger(*grid)
     _close(out, rr.reversed_rearrange(ref.out))
+
+
+# ------------------------------------------------------------------ re-entrancy (threading / streams)
+def test_two_layer_calls_in_flight_on_two_streams():
+    """Two layer calls on two CUDA streams with different inputs, enqueued back to back with no synchronisation between
+    them (the two CFG branches of a sampler step), plus a second round with the streams swapped: every result equals
+    the one computed alone.  Workspace (item counter, parked pooled tiles, gathered copies) and the fork/join side
+    stream are per caller stream."""
+    import threading
+    from video_blade_b200.asa import AsaEngine, AsaKnobs
+    grid = (26, 15, 8)
+    S, H, D = grid[0] * grid[1] * grid[2], 4, 128
+    eng = AsaEngine(AsaKnobs.wan(width=grid[0], height=grid[1], depth=grid[2], max_retain_ratio=0.3))
+    ins = [tuple(x.cuda() for x in O.synth_qkv(1, H, S, D, seed=70 + i, structured=2.0 * i, grid=grid)) for i in range(2)]
+    alone = [eng.forward(*ins[i])[0].clone() for i in range(2)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rnd in range(3):
+        outs = [None, None]
+        for i in range(2):
+            with torch.cuda.stream(streams[(i + rnd) % 2]):
+                for _ in range(3):                                   # several calls per stream keep both queues busy
+                    outs[i] = eng.forward(*ins[i])[0]
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert torch.equal(outs[i], alone[i]), (rnd, i)
+    # two host threads, one stream each
+    res = [None, None]
+
+    def work(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(4):
+                res[i] = eng.forward(*ins[i])[0]
+        streams[i].synchronize()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for i in range(2):
+        assert torch.equal(res[i], alone[i]), i

@@ -156,7 +156,10 @@ class AsaEngine:
         return self._src_row[key]
 
     def workspace(self, device, nbytes: int) -> torch.Tensor:
-        key = str(device)
+        """Scratch for one layer call (gathered copies, means, lists, the attention item counter and parked tiles).
+        One buffer per (device, CUDA stream): calls on the same stream are ordered and may share it; calls in flight
+        on different streams (CFG branches, worker threads) must not, and do not."""
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
         cur = self._ws.get(key)
         if cur is None or cur.numel() < nbytes:
             cur = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)

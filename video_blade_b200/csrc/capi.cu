@@ -3,6 +3,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include <stdlib.h>
@@ -91,26 +93,31 @@ static void gilbert_fill(int W, int H, int D, int64_t* curve2raster) {
   }
 }
 
-// side stream + events for the fork/join inside blade_asa_forward (created once per process and device).  The side
-// stream has the HIGHEST priority: it carries the short latency-bound score and selection kernels, whose CTAs the
-// block scheduler then places ahead of the pending CTAs of the grid-filling, DRAM-bound pooling kernel.
+// side stream + events for the fork/join inside blade_asa_forward: one set PER CALLER STREAM (created on first use, kept
+// for the life of the process), so that layer calls in flight on different streams -- the two CFG branches of a
+// sampler step, or two host threads -- never share a side stream or an event.  Calls on the SAME stream are ordered by
+// the stream itself.  The side stream has the HIGHEST priority: it carries short kernels whose CTAs the block
+// scheduler then places ahead of the pending CTAs of a grid-filling, DRAM-bound kernel on the caller's stream.
 struct ForkState {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-static ForkState* fork_state() {
-  static ForkState st[16];
+static ForkState* fork_state(cudaStream_t caller) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, ForkState> table;
   int dev = 0;
   cudaGetDevice(&dev);
-  ForkState* f = &st[dev & 15];
-  if (!f->side) {
+  const uint64_t key = (static_cast<uint64_t>(dev) << 56) ^ reinterpret_cast<uint64_t>(caller);
+  std::lock_guard<std::mutex> lock(mu);
+  ForkState& f = table[key];
+  if (!f.side) {
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, greatest);
-    cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming);
+    cudaStreamCreateWithPriority(&f.side, cudaStreamNonBlocking, greatest);
+    cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming);
   }
-  return f;
+  return &f;   // unordered_map never moves its nodes: the pointer stays valid
 }
 
 // workspace carving for blade_asa_forward
@@ -264,7 +271,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):
   // 0 = pooling on the side stream, 1 = score/selection on the (high-priority) side stream, 2 = no fork.
   static const int fork_mode = getenv("BLADE_FORK_MODE") ? atoi(getenv("BLADE_FORK_MODE")) : 0;
-  ForkState* fk = (np && fork_mode != 2) ? fork_state() : nullptr;
+  ForkState* fk = (np && fork_mode != 2) ? fork_state(stream) : nullptr;
   cudaStream_t mstream = stream, pstream = stream;  // streams of the mask kernels / the pooling kernel
   if (fk) {
     if (fork_mode == 1) mstream = fk->side; else pstream = fk->side;

@@ -401,21 +401,22 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 // dynamic smem: (16*(D+nb) + 64*(D+4)) floats
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreRows = 16;
+constexpr int kFusedRows = 16;  // rows per CTA of the fused score + selection kernel (8 was slower: every CTA streams all K means)
 constexpr int kScoreChunk = 64;
-// Body shared by score_meanpool_kernel and the fused score + selection kernel: leaves the CTA's 16 softmax rows in
-// shared memory (srow, [16][nb]) and, if `scores` is given, writes them to global memory.
-template <int D>
-__device__ __forceinline__ void score_rows_16(const float* __restrict__ qm, const float* __restrict__ km,
+// Body shared by score_meanpool_kernel (R = 16 rows per CTA) and the fused score + selection kernel (R = 8: twice the
+// CTAs, one selection row per warp): leaves the CTA's R softmax rows in shared memory (srow, [R][nb]) and, if `scores` is given, writes them to global memory.
+template <int D, int R>
+__device__ __forceinline__ void score_rows(const float* __restrict__ qm, const float* __restrict__ km,
                                               float* __restrict__ scores, int nb, float scale, float* sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int DP = D + 4;
   constexpr int d4n = D / 4;
   float* sq = sm;                                  // [16][D]
-  float* srow = sm + kScoreRows * D;               // [16][nb]
-  float* sk = sm + kScoreRows * (D + nb);          // [64][DP]
-  const int i0 = blockIdx.x * kScoreRows;
+  float* srow = sm + R * D;               // [16][nb]
+  float* sk = sm + R * (D + nb);          // [64][DP]
+  const int i0 = blockIdx.x * R;
   const int64_t bh = blockIdx.y;
-  for (int e = threadIdx.x; e < kScoreRows * d4n; e += 256) {
+  for (int e = threadIdx.x; e < R * d4n; e += 256) {
     const int r = e / d4n, c = e % d4n;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i0 + r < nb) v = __ldg(reinterpret_cast<const float4*>(qm + (bh * nb + i0 + r) * D) + c);
@@ -447,17 +448,18 @@ __device__ __forceinline__ void score_rows_16(const float* __restrict__ qm, cons
     if (j0 + kScoreChunk < nb) fetch(j0 + kScoreChunk);
     if (j0 + kk < nb) {
       const float4* kr = reinterpret_cast<const float4*>(sk + kk * DP);
-      const float4* qr = reinterpret_cast<const float4*>(sq + 4 * qg * D);
-      float acc[4][4];
+      constexpr int A = R / 4;                     // query rows per thread group (4 groups of 64 threads)
+      const float4* qr = reinterpret_cast<const float4*>(sq + A * qg * D);
+      float acc[A][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < A; ++a)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
 #pragma unroll 2
       for (int c = 0; c < d4n; ++c) {
         const float4 kv = kr[c];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < A; ++a) {
           const float4 qv = qr[a * d4n + c];
           acc[a][0] = fmaf(qv.x, kv.x, acc[a][0]);
           acc[a][1] = fmaf(qv.y, kv.y, acc[a][1]);
@@ -466,14 +468,14 @@ __device__ __forceinline__ void score_rows_16(const float* __restrict__ qm, cons
         }
       }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        srow[(4 * qg + a) * nb + j0 + kk] = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) * scale;
+      for (int a = 0; a < A; ++a)
+        srow[(A * qg + a) * nb + j0 + kk] = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) * scale;
     }
   }
   __syncthreads();
   // row softmax: two rows per warp
-  for (int rr = 0; rr < kScoreRows / 8; ++rr) {
-    const int r = warp * (kScoreRows / 8) + rr;
+  for (int rr = 0; rr < (R / 8); ++rr) {
+    const int r = warp * ((R / 8)) + rr;
     const int i = i0 + r;
     if (i >= nb) break;
     float* row = srow + r * nb;
@@ -503,7 +505,7 @@ template <int D>
 __global__ void __launch_bounds__(256, 3) score_meanpool_kernel(const float* __restrict__ qm, const float* __restrict__ km,
                                                              float* __restrict__ scores, int nb, float scale) {
   extern __shared__ __align__(16) float sm[];
-  score_rows_16<D>(qm, km, scores, nb, scale, sm);
+  score_rows<D, kScoreRows>(qm, km, scores, nb, scale, sm);
 }
 
 template <int E>
@@ -516,7 +518,7 @@ __device__ __forceinline__ int select_row_bitonic(const float* src, int nk, int 
 // it.  Same arithmetic, bit for bit, as score_meanpool_kernel followed by select_bitonic_kernel<E> (the selection reads
 // the rows from shared memory instead of global).  dynamic smem: the score part + 8 warps * (N doubles + N ints).
 template <int D, int E>
-__global__ void __launch_bounds__(256, 2) score_select_kernel(const float* __restrict__ qm, const float* __restrict__ km,
+__global__ void __launch_bounds__(256, 3) score_select_kernel(const float* __restrict__ qm, const float* __restrict__ km,
                                                            float* __restrict__ scores_opt, int nb, float scale, int lo,
                                                            int hi, float thr, int force_last, int rounding,
                                                            int32_t* __restrict__ idx, int32_t* __restrict__ cnt,
@@ -526,19 +528,21 @@ __global__ void __launch_bounds__(256, 2) score_select_kernel(const float* __res
   extern __shared__ __align__(16) float sm[];
   // programmatic dependent launch: everything above the first global read may overlap the producer's tail
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  score_rows_16<D>(qm, km, scores_opt, nb, scale, sm);
+  score_rows<D, kFusedRows>(qm, km, scores_opt, nb, scale, sm);
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* srow = sm + kScoreRows * D;
-  const size_t score_floats = static_cast<size_t>(kScoreRows) * (D + nb) + kScoreChunk * (D + 4);
-  double* sorted = reinterpret_cast<double*>(sm + ((score_floats + 1) & ~size_t(1))) + warp * 2 * N;
+  const float* srow = sm + kFusedRows * D;
+  // the selection scratch (8 warps x (N doubles + N ints) <= 24 KB) aliases the K-means chunk buffer (64 x (D+4) floats
+  // >= 17 KB for D = 64, 33 KB for D = 128), dead once the scores are in srow; what does not fit follows the score region
+  const size_t srow_end = static_cast<size_t>(kFusedRows) * (D + nb);
+  double* sorted = reinterpret_cast<double*>(sm + ((srow_end + 1) & ~size_t(1))) + warp * 2 * N;
   int* flag = reinterpret_cast<int*>(sorted + N);
   const int64_t bh = blockIdx.y;
   int total = 0;
-  for (int rr = 0; rr < kScoreRows / 8; ++rr) {
-    const int r = warp * (kScoreRows / 8) + rr;
-    const int qi = blockIdx.x * kScoreRows + r;
+  for (int rr = 0; rr < kFusedRows / 8; ++rr) {
+    const int r = warp * (kFusedRows / 8) + rr;
+    const int qi = blockIdx.x * kFusedRows + r;
     if (qi >= nb) break;
     const int64_t row = bh * nb + qi;
     const int base = select_row_bitonic<E>(srow + r * nb, nb, qi, nb, lo, hi, thr, force_last, rounding, sorted, flag,
@@ -1043,8 +1047,10 @@ int blade::score_select_impl(const float* q_mean, const float* k_mean, float* sc
                              cudaStream_t stream, bool pdl) {
   if (nb > 256 || (D != 64 && D != 128)) return -1;
   const int E = nb <= 32 ? 1 : (nb <= 64 ? 2 : (nb <= 128 ? 4 : 8));
-  const size_t score_floats = static_cast<size_t>(kScoreRows) * (D + nb) + kScoreChunk * (D + 4);
-  const size_t smem = ((score_floats + 1) & ~size_t(1)) * sizeof(float) + 8 * (2 * 32 * E) * sizeof(double);
+  const size_t srow_end = ((static_cast<size_t>(kFusedRows) * (D + nb) + 1) & ~size_t(1)) * sizeof(float);
+  const size_t chunk_bytes = static_cast<size_t>(kScoreChunk) * (D + 4) * sizeof(float);
+  const size_t sel_bytes = 8 * (2 * 32 * E) * sizeof(double);
+  const size_t smem = srow_end + (chunk_bytes > sel_bytes ? chunk_bytes : sel_bytes) + 16;
   if (smem > 200 * 1024) return -1;
   BLADE_REQUIRE(cfg->min_retain >= 1 && cfg->max_retain >= 1, BLADE_ERR_ARG, "retain bounds must be >= 1");
   BLADE_REQUIRE(cfg->select_rounding >= 0 && cfg->select_rounding <= 2, BLADE_ERR_ARG, "select_rounding %d not in {0,1,2}",
@@ -1052,7 +1058,7 @@ int blade::score_select_impl(const float* q_mean, const float* k_mean, float* sc
   StageTimer t1(1, stream);   // the fused launch is reported as stage 1 (scores); stage 2 (select) collapses to ~0
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3(static_cast<unsigned>(ceil_div(nb, kScoreRows)), static_cast<unsigned>(B * H));
+  lc.gridDim = dim3(static_cast<unsigned>(ceil_div(nb, kFusedRows)), static_cast<unsigned>(B * H));
   lc.blockDim = dim3(256);
   lc.dynamicSmemBytes = smem;
   lc.stream = stream;
