@@ -41,4 +41,17 @@ with torch.no_grad():
         rel = float(d.norm() / ref[:, sl].norm())
         print(f"rank {rank} fuse={fuse}: ulysses processor vs single-GPU torch norm+rope: rel-L2 {rel:.3e}", flush=True)
         assert rel < 1e-2
+    # the peer-memory data plane: projections written into the symmetric buffer, statistic pushed to the peers, rows
+    # pulled by the gather kernel, output rows pushed by the attention epilogue (B = 2: one sequence after the other)
+    from video_blade_b200.ulysses import UlyssesPeerPlane
+    plane = UlyssesPeerPlane(ug, S // world, heads, D, dtype=torch.bfloat16, device=dev)
+    proc = UlyssesWanAttnProcessor(ug, fuse=True, plane=plane)
+    proc.full_rotary_emb = rope
+    attn.set_processor(proc)
+    for rep in range(3):                                  # repeated: buffer reuse across layers is barrier-ordered
+        got = attn(x[:, sl], rotary_emb=rope[:, :, sl]).float()
+        d = got - ref[:, sl]
+        rel = float(d.norm() / ref[:, sl].norm())
+        print(f"rank {rank} peer plane (rep {rep}): vs single-GPU torch norm+rope: rel-L2 {rel:.3e}", flush=True)
+        assert rel < 1e-2
 dist.destroy_process_group()

@@ -65,8 +65,11 @@ class UlyssesWanAttnProcessor(WanAttnProcessor2_0):
                                            attn.norm_k.weight.detach()[sl], float(attn.norm_q.eps), pl.rstd.view(-1)),
                                   selected_acc=attn.inner_attention.counter(x.device))
             attn.inner_attention.count_call(cnt)
-            outs.append(o.reshape(1, pl.Sl, pl.H * D))
-        o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)          # len 1: to_out reads the symmetric buffer in place
+            o = o.reshape(1, pl.Sl, pl.H * D)
+            # B = 1 (the CFG-split clip): to_out reads the symmetric buffer in place.  B > 1: the next sequence's peers
+            # overwrite it after their next barrier, so keep a copy (stream-ordered before my side of that barrier)
+            outs.append(o if hidden_states.shape[0] == 1 else o.clone())
+        o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return attn.to_out[1](attn.to_out[0](o.type_as(hidden_states)))
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
