@@ -279,8 +279,8 @@ def run_blade(args):
     if world == 1:
         n_seq, P, gid, pr = 1, 1, 0, 0
     else:
-        assert world % 2 == 0, "N > 1 runs the CFG pair: N must be even"
-        n_seq, P = 2, world // 2
+        assert world % args.groups == 0, "N must be a multiple of --groups"
+        n_seq, P = args.groups, world // args.groups
         gid, pr = rank // P, rank % P
         assert H % P == 0 and S % P == 0, f"Ulysses degree {P} does not divide heads {H} / tokens {S}"
     Sl, Hl = S // P, H // P
@@ -450,13 +450,42 @@ def run_blade(args):
             results[name] = {"ms_per_layer_pair": float(tt.item()),
                              "parity": {"bit_exact": bool(par[0].item() == 1.0),
                                         "rel_l2": float((par[1] / par[2]).sqrt().item()), "max_abs": float(mx.item())}}
+        # stage breakdown of the peer-plane layer on this rank (events inside the C call + around the two barriers)
+        if "p2p" in modes:
+            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in STAGES]
+            bev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            acc = {n: 0.0 for n in STAGES}
+            acc.update({"barrier_in": 0.0, "barrier_out": 0.0, "total": 0.0})
+            for i in range(args.steps):
+                flush.zero_()
+                for s_i in range(len(STAGES)):
+                    sev[s_i][0].record(); sev[s_i][1].record()
+                    lib.blade_profile_events(s_i, sev[s_i][0].cuda_event, sev[s_i][1].cuda_event)
+                bev[0].record()
+                plane.barrier()
+                bev[1].record()
+                q_, k_, v_ = plane.views()
+                pe_, out_ = plane.launch_args()
+                eng.forward(q_, k_, v_, peers=pe_, out=out_)
+                bev[2].record()
+                plane.barrier()
+                bev[3].record()
+                torch.cuda.synchronize()
+                for s_i, n in enumerate(STAGES):
+                    acc[n] += sev[s_i][0].elapsed_time(sev[s_i][1])
+                acc["barrier_in"] += bev[0].elapsed_time(bev[1])
+                acc["barrier_out"] += bev[2].elapsed_time(bev[3])
+                acc["total"] += bev[0].elapsed_time(bev[3])
+            for s_i in range(len(STAGES)):
+                lib.blade_profile_events(s_i, None, None)
+            results["p2p"]["rank0_stage_ms"] = {k_: v_ / args.steps for k_, v_ in acc.items()}
         plane_name = min(results, key=lambda n: results[n]["ms_per_layer_pair"])
         pair_ms = results[plane_name]["ms_per_layer_pair"]
         parity = results[plane_name]["parity"]
         shard_bytes = Sl * H * D * 2
-        ulysses = {"parallelism": f"cfg2xulysses{P}", "global_batch": 2, "data_planes": results, "chosen": plane_name,
+        ulysses = {"parallelism": f"cfg{n_seq}xulysses{P}", "global_batch": n_seq, "data_planes": results, "chosen": plane_name,
                    "bytes_exchanged_per_rank": int((3 + 1) * shard_bytes * (P - 1) / P),
-                   "single_gpu_pair_ms": 2 * single_ms}
+                   "single_gpu_pair_ms": n_seq * single_ms}
 
     # ---- section B: e2e through host buffers; every step copies its q,k,v from pinned host memory and reads its
     # output back.  The three stages run on three streams with double-buffered device tensors (step i+1's H2D and
@@ -556,7 +585,7 @@ def run_blade(args):
         n_kernels = 5 + (2 if kn.estimator == "sampled_max" else 0)
         cfg = base_config(args, wname)
         cfg.update({"global_batch": n_seq,
-                    "parallelism": "single" if world == 1 else f"cfg2xulysses{P}",
+                    "parallelism": "single" if world == 1 else f"cfg{n_seq}xulysses{P}",
                     "data_plane": plane_name,
                     "l2": "256 MiB flush between timed iterations", "retained_blocks_per_row": retained,
                     "algorithmic_tflop_per_step": total_flops / 1e12,
@@ -619,6 +648,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clip", action="store_true", help="skip the 8-step clip (BASELINE metric part 2)")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: NCCL all-to-all data plane only")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="N > 1: number of independent sequences (CFG branches); Ulysses degree = N / groups.  The "
+                         "contract run uses 2 (the CFG pair); 1 is a diagnostic (one sequence over all N GPUs)")
     ap.add_argument("--workload", default="wan", choices=["wan", "cog"],
                     help="wan = BASELINE config 2 (default, the headline); cog = config 4")
     ap.add_argument("--retain", type=float, default=None, help="config 5 density sweep: min = max retain ratio")

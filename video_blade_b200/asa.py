@@ -430,7 +430,7 @@ class AsaEngine:
                 cfg.token_row = tok.data_ptr()
         nbytes = self.lib.blade_asa_workspace_bytes(B, H, S, D, C.byref(cfg))
         ws = self.workspace(dev, nbytes)
-        if peers is not None:
+        if peers is not None and out is None:
             out_t = q                                              # layout descriptor only: rows go to peers.out[*]
         else:
             out_t = out if out is not None else torch.empty(B, S, H, D, dtype=q.dtype, device=dev).transpose(1, 2)
@@ -449,7 +449,7 @@ class AsaEngine:
             C.byref(cfg), ptr(scores), C.byref(tensor_desc(out_t)), ptr(sc_out), ptr(mask), ptr(idx), cnt.data_ptr(),
             ws.data_ptr(), ws.numel(), current_stream()))
         del keep
-        res = None if peers is not None else out_t
+        res = None if (peers is not None and out is None) else out_t
         if return_debug:
             return res, dict(scores=sc_out, mask=mask.bool(), idx=idx, cnt=cnt)
         return res, cnt

@@ -9,6 +9,8 @@ act on one head's full sequence -- so head sharding is exact.  The exchange is o
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -155,11 +157,27 @@ class UlyssesPeerPlane:
                                               self._rstd_ptrs, self.P, self.S, self.g.rank_in_group * self.Sl,
                                               current_stream()))
 
+    def launch_args(self):
+        """(peers, out) for AsaEngine.forward.  BLADE_PEER_NO_PUSH=1 (diagnostic): the output stays local instead of
+        being stored into the peers' buffers -- isolates what the NVLink stores cost the attention epilogue."""
+        if not os.environ.get("BLADE_PEER_NO_PUSH"):
+            return self.peers, None
+        from ._lib import BladePeers
+        pe = BladePeers()
+        pe.n_peers, pe.my_peer, pe.rows_per_peer = self.peers.n_peers, self.peers.my_peer, self.peers.rows_per_peer
+        for p in range(self.P):
+            pe.q[p], pe.k[p], pe.v[p] = self.peers.q[p], self.peers.k[p], self.peers.v[p]
+        if getattr(self, "_local_out", None) is None:
+            self._local_out = torch.empty(1, self.S, self.Hl, self.D, dtype=self.qkv.dtype,
+                                          device=self.qkv.device).transpose(1, 2)
+        return pe, self._local_out
+
     def attention(self, eng, **kw):
         """barrier -> layer (pull q/k/v, push out) -> barrier.  Returns my [Sl, H, D] output buffer (valid on the
         current stream after the call)."""
         self.barrier()                                                   # every peer's q/k/v (and rstd) are written
         q, k, v = self.views()
-        _, cnt = eng.forward(q, k, v, peers=self.peers, **kw)
+        pe, out = self.launch_args()
+        _, cnt = eng.forward(q, k, v, peers=pe, out=out, **kw)
         self.barrier()                                                   # every peer's output rows have landed
         return self.out, cnt
