@@ -266,7 +266,8 @@ int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, const BladeTen
  * Reference (under cogvideox/sample_evaluate/Triton/): cogvideo_newattn.py (N) and the Triton kernels
  * kernels/block_sparse_attn_kernel_with_backward_9_10.py (K9).  A block-mask entry is a LEVEL: 0 = skip, 1 = the
  * block's 128 keys, L in {2,4,8} = its 128/L mean-pooled keys/values with `+ log L` on the scaled score; one softmax
- * per query row (K9:135-277, 339-692).  Forward only (the backward, K9:695-1237, is not built).
+
+ * per query row (K9:135-277, 339-692).
  *
  *   reference interface                                           replaced by
  *   pooling x3 over the padded K, V       (K9:1252-1270, 1307-1316)   blade_multilevel_pyramid
@@ -297,6 +298,21 @@ int blade_multilevel_attn_fwd(const BladeTensor* q, const BladeTensor* k, const 
                               const int32_t* idx, const int32_t* cnt4, int64_t idx_stride, BladeTensor* out,
                               float* lse, const int32_t* dst_row, float softmax_scale, void* workspace,
                               size_t ws_bytes, void* stream);
+
+/* Backward of blade_multilevel_attn_fwd (replaces the Triton backward kernels K9:695-1237 / launch K9:1375-1576 behind
+ * `sparse_attention_fn`): given the forward's inputs, its output `out`, its natural-log `lse` and the incoming gradient
+ * `d_out` ([B,H,S,D], any strides), writes dq / dk / dv (tensor dtype, any strides).  The gradient through the pooled
+ * K/V copies is folded back onto k and v (pair means; the pyramid's intermediate roundings are treated as identity,
+ * like the reference's autograd).  Workspace: blade_multilevel_bwd_workspace_bytes (fp32 accumulators per level, zeroed
+ * by the call; 1 KiB aligned). */
+size_t blade_multilevel_bwd_workspace_bytes(int64_t B, int64_t H, int64_t S, int64_t Sk, int64_t D);
+int blade_multilevel_attn_bwd(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v,
+                              const BladeTensor* k2, const BladeTensor* v2, const BladeTensor* k4,
+                              const BladeTensor* v4, const BladeTensor* k8, const BladeTensor* v8,
+                              const int32_t* idx, const int32_t* cnt4, int64_t idx_stride,
+                              const BladeTensor* out, const BladeTensor* d_out, const float* lse,
+                              float softmax_scale, BladeTensor* dq, BladeTensor* dk, BladeTensor* dv,
+                              void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- measurement hook ------------------------------------------------------------------------
  * When set, the library records the given cudaEvent_t pair (passed as void*) on the caller's stream

@@ -185,3 +185,71 @@ def test_layer_matches_reference_module_golden():
     d = (out.float().cpu() - want).abs()
     print(f"[multilevel layer vs reference module fp32] mean_abs={float(d.mean()):.2e} level agreement={agree:.3f}")
     assert float(d.mean()) <= 1e-2 and agree >= 0.7
+
+
+# ------------------------------------------------------------------ backward (K9:695-1237)
+def _grads_oracle(q, k, v, mask, do):
+    qf, kf, vf = (x.float().clone().requires_grad_(True) for x in (q, k, v))
+    o = M.multilevel_attention(qf, kf, vf, mask)
+    o.backward(do.float())
+    return qf.grad, kf.grad, vf.grad
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("S,D,H,seed", [(512, 64, 1, 0), (940, 64, 2, 1), (1560, 128, 2, 2), (300, 128, 1, 3)])
+def test_backward_vs_autograd_through_oracle(S, D, H, seed):
+    """dq, dk, dv of the CUDA backward against autograd through the oracle (which reproduces the reference's own
+    backward kernels to 2e-5, tests/test_oracle_multilevel.py), random level masks incl. level 0 and partly filled
+    pooled tiles, ragged last block (replicate padding folds pooled gradients onto the last token)."""
+    from video_blade_b200 import cogvideo_newattn as N
+    g = torch.Generator().manual_seed(seed)
+    q, k, v = (torch.randn(1, H, S, D, generator=g).bfloat16() for _ in range(3))
+    do = torch.randn(1, H, S, D, generator=g).bfloat16()
+    nb = -(-S // 128)
+    mask = torch.tensor([0, 1, 2, 4, 8])[torch.randint(0, 5, (1, H, nb, nb), generator=g)].to(torch.int32)
+    mask[..., -2:] = 1
+    qc, kc, vc = (x.cuda().requires_grad_(True) for x in (q, k, v))
+    out = N.sparse_attention_fn(qc, kc, vc, mask.cuda())
+    out.backward(do.cuda())
+    wq, wk, wv = _grads_oracle(q, k, v, mask, do)
+    rq, rk, rv = _rel(qc.grad, wq), _rel(kc.grad, wk), _rel(vc.grad, wv)
+    print(f"[multilevel bwd S={S} D={D}] rel-L2 dq {rq:.2e} dk {rk:.2e} dv {rv:.2e}")
+    assert rq <= 2e-2 and rk <= 2e-2 and rv <= 2e-2, (rq, rk, rv)
+    assert torch.isfinite(qc.grad.float()).all() and torch.isfinite(kc.grad.float()).all()
+
+
+def test_backward_vs_reference_kernel_golden():
+    """dq / dk / dv of the reference's own Triton backward kernels (fp32, interpreter; tests/golden/multilevel.npz)."""
+    from video_blade_b200 import cogvideo_newattn as N
+    z, _ = load_npz("multilevel.npz")
+    q, k, v, mask, do = (torch.from_numpy(z[f"bwd_{x}"]) for x in ("q", "k", "v", "mask", "do"))
+    qc, kc, vc = (x.bfloat16().cuda().requires_grad_(True) for x in (q, k, v))
+    out = N.sparse_attention_fn(qc, kc, vc, mask.cuda())
+    out.backward(do.bfloat16().cuda())
+    for name, got in (("dq", qc.grad), ("dk", kc.grad), ("dv", vc.grad)):
+        want = torch.from_numpy(z[f"bwd_{name}"])
+        r = _rel(got, want)
+        print(f"[multilevel bwd golden] {name} rel-L2 {r:.2e}")
+        assert r <= 3e-2, (name, r)
+
+
+def test_backward_levels_zero_one_equals_dense_masked_attention_grad():
+    """mask in {0,1}, S a multiple of 128: gradients of plain block-masked softmax attention (torch autograd, fp32)."""
+    from video_blade_b200 import cogvideo_newattn as N
+    g = torch.Generator().manual_seed(9)
+    S, D = 512, 64
+    q, k, v, do = (torch.randn(1, 2, S, D, generator=g).bfloat16() for _ in range(4))
+    mask = torch.rand(1, 2, 4, 4, generator=g) < 0.5
+    mask |= torch.eye(4, dtype=torch.bool)
+    qc, kc, vc = (x.cuda().requires_grad_(True) for x in (q, k, v))
+    N.sparse_attention_fn(qc, kc, vc, mask.to(torch.uint8).cuda()).backward(do.cuda())
+    qf, kf, vf = (x.float().requires_grad_(True) for x in (q, k, v))
+    tok = mask.repeat_interleave(128, 2).repeat_interleave(128, 3)
+    s = (qf @ kf.transpose(-1, -2)) / D ** 0.5
+    o = torch.softmax(s.masked_fill(~tok, float("-inf")), -1) @ vf
+    o.backward(do.float())
+    assert _rel(qc.grad, qf.grad) <= 2e-2 and _rel(kc.grad, kf.grad) <= 2e-2 and _rel(vc.grad, vf.grad) <= 2e-2

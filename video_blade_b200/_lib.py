@@ -53,6 +53,7 @@ SYMBOLS = [
     "blade_mask64_to_index", "blade_block_sparse_attn64_fwd", "blade_asa_attn64_fwd", "blade_asa_prep_rope",
     "blade_attn_workspace_bytes", "blade_qk_rms_stat", "blade_qk_rms_stat_peers",
     "blade_multilevel_pyramid", "blade_multilevel_mask", "blade_level_mask_to_index", "blade_multilevel_attn_fwd",
+    "blade_multilevel_bwd_workspace_bytes", "blade_multilevel_attn_bwd",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -81,6 +82,9 @@ def load() -> C.CDLL:
     lib.blade_multilevel_pyramid.argtypes = [T, T, vp, vp, vp, vp, vp, vp, vp]
     lib.blade_multilevel_mask.argtypes = [vp, i64, i64, i64, i64, vp, i32, vp, vp, vp, vp]
     lib.blade_level_mask_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
+    lib.blade_multilevel_bwd_workspace_bytes.argtypes = [i64, i64, i64, i64, i64]
+    lib.blade_multilevel_bwd_workspace_bytes.restype = C.c_size_t
+    lib.blade_multilevel_attn_bwd.argtypes = [T, T, T, T, T, T, T, T, T, vp, vp, i64, T, T, vp, f32, T, T, T, vp, C.c_size_t, vp]
     lib.blade_multilevel_attn_fwd.argtypes = [T, T, T, T, T, T, T, T, T, vp, vp, i64, T, vp, vp, f32, vp, C.c_size_t, vp]
     lib.blade_attn_workspace_bytes.argtypes = [i64]
     lib.blade_attn_workspace_bytes.restype = C.c_size_t

@@ -136,6 +136,27 @@ class MultiLevelEngine:
             ws.data_ptr(), ws.numel(), current_stream()))
         return (out, lse) if want_lse else out
 
+    @_on_tensor_device
+    def attention_bwd(self, q, k, v, pyr, idx, cnt4, out, lse, d_out, sm_scale=None):
+        """Backward of `attention` (replaces the Triton backward kernels K9:695-1237): (dq, dk, dv) in q.dtype."""
+        B, H, S, D = q.shape
+        Sk = k.shape[2]
+        dq = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
+        dk = torch.empty(B, Sk, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
+        dv = torch.empty(B, Sk, H, D, dtype=q.dtype, device=q.device).transpose(1, 2)
+        nbytes = int(self.lib.blade_multilevel_bwd_workspace_bytes(B, H, S, Sk, D))
+        ws = self.asa_engine().workspace(q.device, nbytes)
+        scale = (1.0 / math.sqrt(D)) if sm_scale is None else float(sm_scale)
+        if d_out.stride(-1) != 1:
+            d_out = d_out.contiguous()
+        descs = [tensor_desc(t) for pair in pyr for t in pair]
+        check(self.lib.blade_multilevel_attn_bwd(
+            C.byref(tensor_desc(q)), C.byref(tensor_desc(k)), C.byref(tensor_desc(v)), *[C.byref(d) for d in descs],
+            idx.data_ptr(), cnt4.data_ptr(), idx.shape[-1], C.byref(tensor_desc(out)), C.byref(tensor_desc(d_out)),
+            lse.data_ptr(), scale, C.byref(tensor_desc(dq)), C.byref(tensor_desc(dk)), C.byref(tensor_desc(dv)),
+            ws.data_ptr(), ws.numel(), current_stream()))
+        return dq, dk, dv
+
     def forward(self, q, k, v, grid, text_len, ratios, rearrange=True, sample_offsets=None, return_debug=False):
         """AdaptiveBlockSparseAttnTrain.forward (N:237-267) as kernels: gather into curve order (text to the tail) ->
         sampled-max block scores (N:64-90) -> level mask (N:154-207) -> pyramid -> attention with the inverse
@@ -172,10 +193,34 @@ def transfer_attn_to_mask(attn, mask_ratios=None):
     return mask.to(torch.int32)
 
 
+class _MultiLevelAttention(torch.autograd.Function):
+    """The autograd wrapper the reference builds around its Triton kernels (K9:1375-1611): forward = _fwd_kernel,
+    backward = the dq / dk / dv kernels, both replaced by CUDA kernels behind the C ABI."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, sm_scale):
+        e = _engine()
+        qd, kd, vd = q.detach(), k.detach(), v.detach()
+        idx, cnt4 = e.mask_to_index(mask)
+        pyr = e.pyramid(kd, vd)
+        out, lse = e.attention(qd, kd, vd, pyr, idx, cnt4, sm_scale=sm_scale, want_lse=True)
+        ctx.save_for_backward(qd, kd, vd, out, lse, idx, cnt4, *[t for pair in pyr for t in pair])
+        ctx.sm_scale = sm_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qd, kd, vd, out, lse, idx, cnt4, *flat = ctx.saved_tensors
+        pyr = [(flat[0], flat[1]), (flat[2], flat[3]), (flat[4], flat[5])]
+        dq, dk, dv = _engine().attention_bwd(qd, kd, vd, pyr, idx, cnt4, out, lse, d_out.to(qd.dtype), sm_scale=ctx.sm_scale)
+        return dq, dk, dv, None, None
+
+
 def sparse_attention_fn(q, k, v, mask, sm_scale=None):
     """sparse_attention_factory(BLOCK_M=128, BLOCK_N=128) (N:9; K9:1578-1611): multi-level attention on a caller's
-    level mask [B,H,ceil(S/128),ceil(S/128)]."""
-    require_no_grad(q, k, v)
+    level mask [B,H,ceil(S/128),ceil(S/128)].  Differentiable in q, k, v like the reference's autograd function."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
+        return _MultiLevelAttention.apply(q, k, v, mask, sm_scale)
     e = _engine()
     idx, cnt4 = e.mask_to_index(mask)
     return e.attention(q, k, v, e.pyramid(k, v), idx, cnt4, sm_scale=sm_scale)
