@@ -253,3 +253,19 @@ def test_backward_levels_zero_one_equals_dense_masked_attention_grad():
     o = torch.softmax(s.masked_fill(~tok, float("-inf")), -1) @ vf
     o.backward(do.float())
     assert _rel(qc.grad, qf.grad) <= 2e-2 and _rel(kc.grad, kf.grad) <= 2e-2 and _rel(vc.grad, vf.grad) <= 2e-2
+
+
+def test_backward_at_reference_test_shape():
+    """B=1, H=2 of the reference's N=17776, D=64 test shape: backward against autograd through the oracle."""
+    from video_blade_b200 import cogvideo_newattn as N
+    torch.manual_seed(123)
+    B, H, S, D = 1, 2, 17776, 64
+    q, k, v, do = (torch.randn(B, H, S, D).bfloat16() for _ in range(4))
+    nb = -(-S // 128)
+    mask = M.multilevel_mask(torch.softmax(torch.randn(B, H, nb, nb) * 2.0, -1), N.mask_ratios)
+    qc, kc, vc = (x.cuda().requires_grad_(True) for x in (q, k, v))
+    N.sparse_attention_fn(qc, kc, vc, mask.cuda()).backward(do.cuda())
+    wq, wk, wv = _grads_oracle(q, k, v, mask, do)
+    rq, rk, rv = _rel(qc.grad, wq), _rel(kc.grad, wk), _rel(vc.grad, wv)
+    print(f"[multilevel bwd 17776x64] rel-L2 dq {rq:.2e} dk {rk:.2e} dv {rv:.2e}")
+    assert rq <= 2e-2 and rk <= 2e-2 and rv <= 2e-2
