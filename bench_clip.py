@@ -52,7 +52,7 @@ def run_clip(world, rank, dev, steps=8, layers=30, reps=2, model="wan", guidance
             net = CogLikeDiT(layers=layers).to(torch.bfloat16).eval()
         blocks = net.transformer_blocks
         inner = set_block_sparse_attn_cogvideox(net)
-        net.set_sequence_parallel(group)
+        net.set_sequence_parallel(group, data_plane=data_plane)
         noise = torch.randn(1, 13, 16, 60, 90, generator=g).to(dev, torch.bfloat16)
         prompt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
         negative = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)

@@ -22,10 +22,14 @@ txt = torch.randn(1, 226, 4096, generator=g).to(dev, torch.bfloat16)
 t = torch.full((1,), 500.0, device=dev)
 with torch.no_grad():
     ref = model(lat, t, txt)
-    model.set_sequence_parallel(UlyssesGroup(world, rank, world))
-    got = model(lat, t, txt)
-d = (got.float() - ref.float())
-rel = float(d.norm() / ref.float().norm())
-print(f"rank {rank}: ulysses{world} vs single GPU rel-L2 {rel:.3e} max|d| {float(d.abs().max()):.3e} finite {bool(torch.isfinite(got).all())}", flush=True)
-assert rel < 3e-2
+    ug = UlyssesGroup(world, rank, world)
+    for plane in ("nccl", "p2p"):
+        model.set_sequence_parallel(ug, data_plane=plane)
+        for rep in range(2):
+            got = model(lat, t, txt)
+        d = (got.float() - ref.float())
+        rel = float(d.norm() / ref.float().norm())
+        print(f"rank {rank}: ulysses{world} [{model.data_plane_in_use}] vs single GPU rel-L2 {rel:.3e} max|d| "
+              f"{float(d.abs().max()):.3e} finite {bool(torch.isfinite(got).all())}", flush=True)
+        assert rel < 3e-2 and model.data_plane_in_use == plane
 dist.destroy_process_group()

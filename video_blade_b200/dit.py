@@ -129,14 +129,53 @@ class UlyssesCogAttnProcessor:
     the Ulysses exchange around `inner_attention`.  `rope_local` = (cos, sin) [S/P, D] for my tokens, identity rows
     for text tokens (MC:59-64 rotates the video part only)."""
 
-    def __init__(self, group: UlyssesGroup, fuse: bool = True):
+    def __init__(self, group: UlyssesGroup, fuse: bool = True, plane=None):
         self.group = group
         self.fuse = fuse
+        self.plane = plane          # UlyssesPeerPlane: pull q/k/v rows, push output rows over NVLink
         self._table = None
+
+    def _rope_table(self, rope_full, device):
+        cos, sin = rope_full
+        key_ = (cos, sin, cos._version, sin._version)   # held references, not bare addresses
+        if self._table is None or self._table[0][0] is not cos or self._table[0][1] is not sin \
+                or self._table[0][2:] != key_[2:]:
+            self._table = (key_, torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(device, torch.float32).contiguous())
+        return self._table[1]
+
+    def _call_peer_plane(self, attn, hidden_states, rope_full, text_len):
+        """Projections written into the symmetric buffer; per-head LayerNorm, rotary embedding (video rows only) and the
+        curve-order gather with the text rows at the tail all happen in the kernel that pulls the rows from the peers."""
+        from . import cogvideo_blocksparseattn as Cg
+        pl = self.plane
+        eng = Cg._engine(use_rearrange=bool(attn.inner_attention.use_rearrange))
+        nq, nk = attn.norm_q, attn.norm_k
+        outs = []
+        for b in range(hidden_states.shape[0]):
+            x = hidden_states[b]
+            for j, lin in enumerate((attn.to_q, attn.to_k, attn.to_v)):
+                dst = pl.qkv[j].view(pl.Sl, pl.H * pl.D)
+                if lin.bias is not None:
+                    torch.addmm(lin.bias, x, lin.weight.t(), out=dst)
+                else:
+                    torch.mm(x, lin.weight.t(), out=dst)
+            o, cnt = pl.attention(eng, rope=(self._rope_table(rope_full, x.device), int(text_len)),
+                                  qk_norm=(3, nq.weight.detach(), nk.weight.detach(), float(nq.eps), None,
+                                           None if nq.bias is None else nq.bias.detach(),
+                                           None if nk.bias is None else nk.bias.detach()),
+                                  selected_acc=attn.inner_attention.counter(x.device))
+            attn.inner_attention.count_call(cnt)
+            o = o.reshape(1, pl.Sl, pl.H * pl.D)
+            outs.append(o if hidden_states.shape[0] == 1 else o.clone())
+        o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return attn.to_out[1](attn.to_out[0](o.type_as(hidden_states)))
 
     def __call__(self, attn, hidden_states, rope_local, rope_full=None, text_len=0):
         from .modify_cogvideo import _norm_fusable, apply_rotary_emb as cog_rope
         B, Sl, _ = hidden_states.shape
+        if self.plane is not None and self.fuse and rope_full is not None and hidden_states.is_cuda \
+                and _norm_fusable(attn, hidden_states.view(B, Sl, attn.heads, -1), hidden_states.shape[-1] // attn.heads):
+            return self._call_peer_plane(attn, hidden_states, rope_full, text_len)
         q = attn.to_q(hidden_states).view(B, Sl, attn.heads, -1)
         k = attn.to_k(hidden_states).view(B, Sl, attn.heads, -1)
         v = attn.to_v(hidden_states).view(B, Sl, attn.heads, -1)
@@ -144,13 +183,8 @@ class UlyssesCogAttnProcessor:
         if self.fuse and rope_full is not None and _norm_fusable(attn, q, q.shape[-1]):
             # per-head LayerNorm and the rotary embedding need nothing from other ranks: both run inside the gather
             # kernel on the packed receive buffer (my heads, all tokens); the projections travel untouched
-            cos, sin = rope_full
-            key_ = (cos, sin, cos._version, sin._version)   # held references, not bare addresses
-            if self._table is None or self._table[0][0] is not cos or self._table[0][1] is not sin \
-                        or self._table[0][2:] != key_[2:]:
-                self._table = (key_, torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(q.device, torch.float32).contiguous())
             nq, nk = attn.norm_q, attn.norm_k
-            kw = dict(rotary=(self._table[1], int(text_len)),
+            kw = dict(rotary=(self._rope_table(rope_full, q.device), int(text_len)),
                       qk_norm=(3, nq.weight.detach(), nk.weight.detach(), float(nq.eps), None,
                                None if nq.bias is None else nq.bias.detach(), None if nk.bias is None else nk.bias.detach()))
         else:
@@ -461,9 +495,33 @@ class CogLikeDiT(nn.Module):
         self._rope = {}
         self.group: Optional[UlyssesGroup] = None
 
-    def set_sequence_parallel(self, group: Optional[UlyssesGroup]):
-        """Ulysses degree P: every rank keeps S/P tokens of the concatenated [text ; video] sequence."""
+    def set_sequence_parallel(self, group: Optional[UlyssesGroup], data_plane: str = "auto"):
+        """Ulysses degree P: every rank keeps S/P tokens of the concatenated [text ; video] sequence.
+        data_plane as in WanLikeDiT.set_sequence_parallel."""
         self.group = group
+        self._plane_mode = data_plane
+        self._plane = None
+        self.data_plane_in_use = "none" if group is None or group.P == 1 else "nccl"
+
+    def _ensure_plane(self, Sl, device, dtype):
+        g = self.group
+        if g is None or g.P == 1 or self._plane_mode == "nccl" or self._plane is not None:
+            return
+        import torch.distributed as dist
+        from .ulysses import UlyssesPeerPlane
+        ok, plane = 1, None
+        try:
+            plane = UlyssesPeerPlane(g, Sl, self.heads, self.dim // self.heads, dtype=dtype, device=device)
+        except Exception as e:
+            ok = 0
+            if self._plane_mode == "p2p":
+                raise
+            print(f"[video_blade_b200] peer-memory plane unavailable ({type(e).__name__}: {e}); using NCCL all_to_all")
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self._plane = plane if int(flag.item()) else False
+        if self._plane:
+            self.data_plane_in_use = "p2p"
 
     def _blocks_sequence_parallel(self, x, txt, temb, rope):
         """The transformer blocks on my shard of [text ; video]; returns the full-length video / text streams."""
@@ -479,7 +537,8 @@ class CogLikeDiT(nn.Module):
         D = cos.shape[-1]
         cos_f = torch.cat([torch.ones(T, D, device=cos.device), cos])[sl]         # identity for text rows
         sin_f = torch.cat([torch.zeros(T, D, device=sin.device), sin])[sl]
-        proc = UlyssesCogAttnProcessor(g)
+        self._ensure_plane(Sl, x.device, x.dtype)
+        proc = UlyssesCogAttnProcessor(g, plane=self._plane or None)
         for blk in self.transformer_blocks:
             for norm, fn in ((blk.norm1, lambda h, a=blk.attn1: proc(a, h, (cos_f, sin_f), rope_full=rope, text_len=T)),
                              (blk.norm2, blk.ff)):
