@@ -183,7 +183,9 @@ def test_register_budgets_of_the_hot_kernels():
         if "prep_block_kernel" in name:
             seen["prep"] += 1
             assert regs <= 85, (name, regs)
-            assert spill <= 64, (name, spill)
+            peer = re.search(r"Lb([01])E+v", name).group(1) == "1"     # last template argument: Ulysses peer pull
+            # the peer-pull variants (NVLink-bound) index a per-peer pointer table and spill a little more
+            assert spill <= (192 if peer else 64), (name, spill)
         elif "asa_attn_kernel" in name:
             seen["attn"] += 1
             assert regs <= 168 and spill <= 96, (name, regs, spill)
