@@ -247,3 +247,34 @@ def test_wan_processor_installer_defaults_with_each_estimator(estimator):
         assert 0.0 < inner.average_sparsity() < 1.0                       # device counter fed by the selection kernel
     finally:
         W.width, W.height, W.depth, W.max_retain_ratio, W.estimator = 52, 30, 21, 0.17, "meanpool"
+
+
+@pytest.mark.gpu
+def test_scaffold_fused_glue_matches_torch_expressions():
+    """The benchmark scaffold's fused token-wise kernels (scaffold_ops, not the hot path) against the torch expressions
+    they replace: identical up to one bf16 rounding."""
+    from video_blade_b200 import scaffold_ops as ops
+    torch.manual_seed(0)
+    for C, S in ((1536, 517), (3072, 130), (256, 33)):
+        x = torch.randn(2, S, C, device="cuda").bfloat16()
+        y = torch.randn(2, S, C, device="cuda").bfloat16()
+        sc, sh, g = (torch.randn(2, 1, C, device="cuda") * 0.3 for _ in range(3))
+        want = (torch.nn.functional.layer_norm(x.float(), (C,), eps=1e-6) * (1 + sc) + sh)
+        got = ops.ln_modulate(x, sc, sh, 1e-6)
+        assert got.dtype == x.dtype and float((got.float() - want).abs().max()) <= 2 ** -6
+        assert float((got.float() - want.bfloat16().float()).abs().gt(0).float().mean()) < 0.02
+        want = (x.float() + y.float() * g).bfloat16()
+        got = ops.gated_residual(x, y, g)
+        assert float((got.float() - want.float()).abs().gt(0).float().mean()) < 0.01
+        assert float((got.float() - want.float()).abs().max()) <= 2 ** -5
+        w = (1 + 0.2 * torch.randn(C, device="cuda")).bfloat16()
+        v = x.float()
+        want = (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()).bfloat16()
+        got = ops.rmsnorm(x, w, 1e-6)
+        assert float((got.float() - want.float()).abs().gt(0).float().mean()) < 0.02
+        assert float((got.float() - want.float()).abs().max()) <= 2 ** -5
+    lin = torch.nn.Linear(512, 1024).cuda().bfloat16()
+    xx = torch.randn(3, 77, 512, device="cuda").bfloat16()
+    want = torch.nn.functional.gelu(lin(xx), approximate="tanh")
+    got = ops.linear_gelu_tanh(xx, lin)
+    assert got.shape == want.shape and float((got.float() - want.float()).abs().max()) <= 3e-2

@@ -54,6 +54,7 @@ SYMBOLS = [
     "blade_attn_workspace_bytes", "blade_qk_rms_stat", "blade_qk_rms_stat_peers",
     "blade_multilevel_pyramid", "blade_multilevel_mask", "blade_level_mask_to_index", "blade_multilevel_attn_fwd",
     "blade_multilevel_bwd_workspace_bytes", "blade_multilevel_attn_bwd",
+    "blade_scaffold_ln_modulate", "blade_scaffold_rmsnorm", "blade_scaffold_gated_residual",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -82,6 +83,9 @@ def load() -> C.CDLL:
     lib.blade_multilevel_pyramid.argtypes = [T, T, vp, vp, vp, vp, vp, vp, vp]
     lib.blade_multilevel_mask.argtypes = [vp, i64, i64, i64, i64, vp, i32, vp, vp, vp, vp]
     lib.blade_level_mask_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
+    lib.blade_scaffold_ln_modulate.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, i32, vp]
+    lib.blade_scaffold_rmsnorm.argtypes = [vp, vp, vp, i64, i64, f32, i32, vp]
+    lib.blade_scaffold_gated_residual.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, vp]
     lib.blade_multilevel_bwd_workspace_bytes.argtypes = [i64, i64, i64, i64, i64]
     lib.blade_multilevel_bwd_workspace_bytes.restype = C.c_size_t
     lib.blade_multilevel_attn_bwd.argtypes = [T, T, T, T, T, T, T, T, T, vp, vp, i64, T, T, vp, f32, T, T, T, vp, C.c_size_t, vp]

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libblade_asa.so")
-SOURCES = ["capi.cu", "mask_kernels.cu", "attn_kernel.cu", "estimator_kernel.cu", "multilevel.cu", "multilevel_bwd.cu"]
+SOURCES = ["capi.cu", "mask_kernels.cu", "attn_kernel.cu", "estimator_kernel.cu", "multilevel.cu", "multilevel_bwd.cu", "scaffold_kernels.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "tmap.cuh", os.path.join(ROOT, "include", "blade_asa.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -162,9 +162,8 @@ class RMSNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x):
-        v = x.float()
-        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)
-        return (v * self.weight.float()).type_as(x)
+        from .scaffold_ops import rmsnorm     # fp32 chain, one rounding: one fused pass on CUDA, torch ops elsewhere
+        return rmsnorm(x, self.weight, self.eps)
 
 
 class Attention(nn.Module):
