@@ -318,11 +318,13 @@ int blade_multilevel_attn_bwd(const BladeTensor* q, const BladeTensor* k, const 
  * Fused token-wise glue of the random-init DiT scaffolds that the 8-step clip benchmark times (video_blade_b200/dit.py;
  * in the reference these ops are diffusers' transformer block, around `attn1`).  x, y, out: contiguous [B,S,C] tensors of
  * `dtype` (BLADE_BF16 / BLADE_F16); scale, shift, gate: fp32 [B,C]; C a multiple of 256, at most 4096.
- *   ln_modulate:     out = LayerNorm_without_affine(x) * (1 + scale[b]) + shift[b]     (fp32 arithmetic, one rounding)
+ *   ln_modulate:     out = LayerNorm(x) [* weight + bias] * (1 + scale[b]) + shift[b]  (fp32 arithmetic, one rounding;
+ *                    weight / bias [C] in `dtype`, NULL = no affine)
  *   rmsnorm:         out = x * rsqrt(mean(x^2) + eps) * weight                          (weight [C] in `dtype`)
  *   gated_residual:  out = x + y * gate[b] */
-int blade_scaffold_ln_modulate(const void* x, const float* scale, const float* shift, void* out, int64_t B, int64_t S,
-                               int64_t C, float eps, int32_t dtype, void* stream);
+int blade_scaffold_ln_modulate(const void* x, const float* scale, const float* shift, const void* weight,
+                               const void* bias, void* out, int64_t B, int64_t S, int64_t C, float eps, int32_t dtype,
+                               void* stream);
 int blade_scaffold_rmsnorm(const void* x, const void* weight, void* out, int64_t rows, int64_t C, float eps,
                            int32_t dtype, void* stream);
 int blade_scaffold_gated_residual(const void* x, const void* y, const float* gate, void* out, int64_t B, int64_t S,

@@ -265,6 +265,9 @@ def test_scaffold_fused_glue_matches_torch_expressions():
             return bool(((a.float() - b.float()).abs() <= b.float().abs() * 2.0 ** -7 + 1e-6).all())
         assert got.dtype == x.dtype and one_ulp(got, want)
         assert float((got.float() - want.bfloat16().float()).abs().gt(0).float().mean()) < 0.02
+        lw, lb = (1 + 0.2 * torch.randn(C, device="cuda")).bfloat16(), (0.1 * torch.randn(C, device="cuda")).bfloat16()
+        want = torch.nn.functional.layer_norm(x.float(), (C,), lw.float(), lb.float(), eps=1e-5) * (1 + sc) + sh
+        assert one_ulp(ops.ln_modulate(x, sc, sh, 1e-5, lw, lb), want)      # affine variant (CogVideoX LayerNormZero)
         want = (x.float() + y.float() * g).bfloat16()
         got = ops.gated_residual(x, y, g)
         assert float((got.float() - want.float()).abs().gt(0).float().mean()) < 0.01

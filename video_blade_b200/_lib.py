@@ -83,7 +83,7 @@ def load() -> C.CDLL:
     lib.blade_multilevel_pyramid.argtypes = [T, T, vp, vp, vp, vp, vp, vp, vp]
     lib.blade_multilevel_mask.argtypes = [vp, i64, i64, i64, i64, vp, i32, vp, vp, vp, vp]
     lib.blade_level_mask_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
-    lib.blade_scaffold_ln_modulate.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, i32, vp]
+    lib.blade_scaffold_ln_modulate.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, i32, vp]
     lib.blade_scaffold_rmsnorm.argtypes = [vp, vp, vp, i64, i64, f32, i32, vp]
     lib.blade_scaffold_gated_residual.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, vp]
     lib.blade_multilevel_bwd_workspace_bytes.argtypes = [i64, i64, i64, i64, i64]

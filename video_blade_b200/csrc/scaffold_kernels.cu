@@ -3,7 +3,7 @@
 // to diffusers' WanTransformerBlock (adaLN modulation in fp32 around every sub-layer); eager PyTorch runs each of them as
 // 5-7 passes over [B,S,C] in fp32 (28-30 bytes per element), which made the glue -- not attention, not the GEMMs -- the
 // largest share of the clip (profiles/r02_profile_clip_before_fused_glue.txt: 48 % of a block).  One pass each here.
-//   blade_scaffold_ln_modulate     out = bf16( LayerNorm_noaffine(float(x)) * (1 + scale[b]) + shift[b] )
+//   blade_scaffold_ln_modulate     out = bf16( LayerNorm(float(x))[* w + b] * (1 + scale[b]) + shift[b] )
 //   blade_scaffold_gated_residual  out = bf16( float(x) + float(y) * gate[b] )
 //   blade_scaffold_rmsnorm         out = bf16( float(x) * rsqrt(mean(float(x)^2) + eps) * float(w) )
 // x, y, out: [B, S, C] contiguous 16-bit; scale / shift / gate: fp32 [B, C]; C a multiple of 256, C <= 4096.
@@ -51,7 +51,8 @@ constexpr int kMaxChunks = 16;  // 16-byte chunks per lane: C <= 32 * 16 * 8 = 4
 template <bool IS_BF16, int MODE, int NCH>
 __global__ void __launch_bounds__(256) norm_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, const uint16_t* __restrict__ w16,
-                                                        uint16_t* __restrict__ out, int64_t rows, int S, int C, float eps) {
+                                                        const uint16_t* __restrict__ b16, uint16_t* __restrict__ out,
+                                                        int64_t rows, int S, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
@@ -100,8 +101,22 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(const uint16_t* __restri
         const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        float wf[8], bf_[8];
+        if (w16) {  // affine LayerNorm (CogVideoX's LayerNormZero): ((x - mean) * rstd * w + b), then the modulation
+          sc_unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>(w16 + col)), wf);
+          if (b16) {
+            sc_unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>(b16 + col)), bf_);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, 1.0f + sc[i], sh[i]);
+            for (int i = 0; i < 8; ++i) bf_[i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float n = (v[c][i] - mean) * rstd;
+          if (w16) n = fmaf(n, wf[i], bf_[i]);
+          o[i] = fmaf(n, 1.0f + sc[i], sh[i]);
+        }
       } else {
         float wf[8];
         sc_unpack8<IS_BF16>(__ldg(reinterpret_cast<const uint4*>(w16 + col)), wf);
@@ -146,15 +161,18 @@ static int check_scaffold(const void* a, int64_t B, int64_t S, int64_t C, int dt
 
 using namespace blade;
 
-extern "C" int blade_scaffold_ln_modulate(const void* x, const float* scale, const float* shift, void* out, int64_t B,
-                                          int64_t S, int64_t C, float eps, int32_t dtype, void* stream_) {
+extern "C" int blade_scaffold_ln_modulate(const void* x, const float* scale, const float* shift, const void* weight,
+                                          const void* bias, void* out, int64_t B, int64_t S, int64_t C, float eps,
+                                          int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = check_scaffold(x, B, S, C, dtype)) return e;
   BLADE_REQUIRE(scale && shift && out, BLADE_ERR_ARG, "null pointer");
   const int64_t rows = B * S;
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
 #define LAUNCH_LN(BF, N_)                                                                                          \
-  norm_rows_kernel<BF, 0, N_><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), scale, shift, nullptr,   \
+  norm_rows_kernel<BF, 0, N_><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), scale, shift,            \
+                                                        static_cast<const uint16_t*>(weight),                     \
+                                                        static_cast<const uint16_t*>(bias),                       \
                                                         static_cast<uint16_t*>(out), rows, (int)S, (int)C, eps)
   const bool bf = dtype == BLADE_BF16;
   const int nch = (int)(C / 256);
@@ -174,7 +192,7 @@ extern "C" int blade_scaffold_rmsnorm(const void* x, const void* weight, void* o
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
 #define LAUNCH_RMS(BF, N_)                                                                                         \
   norm_rows_kernel<BF, 1, N_><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), nullptr, nullptr,        \
-                                                        static_cast<const uint16_t*>(weight),                     \
+                                                        static_cast<const uint16_t*>(weight), nullptr,            \
                                                         static_cast<uint16_t*>(out), rows, (int)rows, (int)C, eps)
   const bool bf = dtype == BLADE_BF16;
   const int nch = (int)(C / 256);

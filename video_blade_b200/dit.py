@@ -453,9 +453,10 @@ class _LayerNormZero(nn.Module):
         self.norm = nn.LayerNorm(dim, eps=1e-5, elementwise_affine=True)
 
     def forward(self, x, txt, temb):
+        from . import scaffold_ops as ops
         sh, sc, g, tsh, tsc, tg = self.linear(F.silu(temb)).chunk(6, dim=1)
-        x = self.norm(x) * (1 + sc[:, None]) + sh[:, None]
-        txt = self.norm(txt) * (1 + tsc[:, None]) + tsh[:, None]
+        x = ops.ln_modulate(x, sc, sh, self.norm.eps, self.norm.weight, self.norm.bias)      # one fused pass on CUDA
+        txt = ops.ln_modulate(txt, tsc, tsh, self.norm.eps, self.norm.weight, self.norm.bias)
         return x, txt, g[:, None], tg[:, None]
 
 
@@ -470,11 +471,12 @@ class CogBlock(nn.Module):
     def forward(self, x, txt, temb, rope):
         T = txt.shape[1]
         nx, nt, g, tg = self.norm1(x, txt, temb)
+        from . import scaffold_ops as ops
         ax, at = self.attn1(nx, encoder_hidden_states=nt, image_rotary_emb=rope)
-        x, txt = x + g * ax, txt + tg * at
+        x, txt = ops.gated_residual(x, ax, g), ops.gated_residual(txt, at, tg)
         nx, nt, g, tg = self.norm2(x, txt, temb)
-        ff = self.ff(torch.cat([nt, nx], dim=1))
-        return x + g * ff[:, T:], txt + tg * ff[:, :T]
+        ff = self.ff[2](ops.linear_gelu_tanh(torch.cat([nt, nx], dim=1), self.ff[0]))
+        return ops.gated_residual(x, ff[:, T:], g), ops.gated_residual(txt, ff[:, :T], tg)
 
 
 def rope_cos_sin(frames, height, width, head_dim, theta=10000.0, device="cpu"):

@@ -16,20 +16,24 @@ def _fusable(x, C):
     return x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and C % 256 == 0 and C <= 4096
 
 
-def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float) -> torch.Tensor:
-    """LayerNorm without affine over the last dim, in fp32, then `* (1 + scale) + shift` (scale / shift [B,1,C] or
-    [B,C], fp32) -> x.dtype."""
+def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float, weight=None, bias=None) -> torch.Tensor:
+    """LayerNorm over the last dim in fp32 (optional affine weight / bias), then `* (1 + scale) + shift` (scale / shift
+    [B,1,C] or [B,C]) -> x.dtype."""
     B, S, C = x.shape
-    if not _fusable(x, C):
-        h = torch.nn.functional.layer_norm(x.float(), (C,), eps=eps)
+    if not _fusable(x, C) or (weight is not None and weight.dtype != x.dtype):
+        h = torch.nn.functional.layer_norm(x.float(), (C,), None if weight is None else weight.float(),
+                                           None if bias is None else bias.float(), eps=eps)
         return (h * (1 + scale.reshape(B, 1, C).float()) + shift.reshape(B, 1, C).float()).type_as(x)
     x = x.contiguous()
     sc = scale.reshape(B, C).float().contiguous()
     sh = shift.reshape(B, C).float().contiguous()
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().blade_scaffold_ln_modulate(x.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), B, S, C,
-                                                          float(eps), _lib._dtype_code(x), _lib.current_stream()))
+        w = None if weight is None else weight.contiguous()
+        b = None if bias is None else bias.contiguous()
+        _lib.check(_lib.load().blade_scaffold_ln_modulate(x.data_ptr(), sc.data_ptr(), sh.data_ptr(), _lib.ptr(w), _lib.ptr(b),
+                                                          out.data_ptr(), B, S, C, float(eps), _lib._dtype_code(x),
+                                                          _lib.current_stream()))
     return out
 
 
