@@ -544,10 +544,28 @@ class CogLikeDiT(nn.Module):
         sin_f = torch.cat([torch.zeros(T, D, device=sin.device), sin])[sl]
         self._ensure_plane(Sl, x.device, x.dtype)
         proc = UlyssesCogAttnProcessor(g, plane=self._plane or None)
+        from . import scaffold_ops as ops
+        n_t = int(is_text.sum())                                # text rows of my shard lead it (text comes first)
+        fused = hs.is_cuda and hs.shape[0] == 1                 # B = 1: the two row ranges are contiguous views
+
+        def per_segment(op, *per_token, text, video):
+            """op on the text rows with the text parameters and on the video rows with the video parameters."""
+            parts = []
+            if n_t:
+                parts.append(op(*[a[:, :n_t] for a in per_token], *text))
+            if n_t < hs.shape[1]:
+                parts.append(op(*[a[:, n_t:] for a in per_token], *video))
+            return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         for blk in self.transformer_blocks:
             for norm, fn in ((blk.norm1, lambda h, a=blk.attn1: proc(a, h, (cos_f, sin_f), rope_full=rope, text_len=T)),
-                             (blk.norm2, blk.ff)):
+                             (blk.norm2, lambda h, ff=blk.ff: ff[2](ops.linear_gelu_tanh(h, ff[0])))):
                 sh, sc, gt, tsh, tsc, tg = norm.linear(F.silu(temb)).chunk(6, dim=1)
+                if fused:
+                    ln = norm.norm
+                    h = per_segment(lambda x_, s_, b_: ops.ln_modulate(x_, s_, b_, ln.eps, ln.weight, ln.bias), hs,
+                                    text=(tsc, tsh), video=(sc, sh))
+                    hs = per_segment(lambda x_, y_, g_: ops.gated_residual(x_, y_, g_), hs, fn(h), text=(tg,), video=(gt,))
+                    continue
                 shift = torch.where(is_text, tsh[:, None], sh[:, None])
                 scale = torch.where(is_text, tsc[:, None], sc[:, None])
                 gate = torch.where(is_text, tg[:, None], gt[:, None])
