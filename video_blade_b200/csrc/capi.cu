@@ -262,15 +262,20 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
   BLADE_CUDA_OK(cudaMemsetAsync(ws + w.park, 0, sizeof(int), stream));
   const bool need_means = scores_in == nullptr && !sampled;
   // gather / rotate / block means on the caller's stream ...
+  // q and k first (the score + selection chain only needs their block means); v's copy runs on the side stream in front
+  // of the pooling, next to the latency-bound score / selection kernel.  BLADE_SPLIT_V=0 restores one launch (A/B).
+  static const bool split_v = !(getenv("BLADE_SPLIT_V") && atoi(getenv("BLADE_SPLIT_V")) == 0);
+  static const int fork_mode0 = getenv("BLADE_FORK_MODE") ? atoi(getenv("BLADE_FORK_MODE")) : 0;
+  const bool v_later = split_v && v_copy && np > 0 && fork_mode0 == 0;
   if (int e = prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
                         v_copy ? ws + w.v_r : nullptr, need_means ? q_mean : nullptr, need_means ? k_mean : nullptr,
                         nullptr, nullptr, cfg->block_size, cfg->sample_gap, cfg->rope_cos_sin, cfg->rope_first_row, 1,
-                        stream, norm_on ? &pn : nullptr, cfg->token_row, cfg->peers))
+                        stream, norm_on ? &pn : nullptr, cfg->token_row, cfg->peers, v_later ? 3 : 7))
     return e;
   // ... then the bandwidth-bound gap pooling and the latency-bound score + selection kernels run concurrently on
   // two streams, joined right before the attention launch (events only, no host sync).  BLADE_FORK_MODE (A/B knob):
   // 0 = pooling on the side stream, 1 = score/selection on the (high-priority) side stream, 2 = no fork.
-  static const int fork_mode = getenv("BLADE_FORK_MODE") ? atoi(getenv("BLADE_FORK_MODE")) : 0;
+  const int fork_mode = fork_mode0;
   ForkState* fk = (np && fork_mode != 2) ? fork_state(stream) : nullptr;
   cudaStream_t mstream = stream, pstream = stream;  // streams of the mask kernels / the pooling kernel
   if (fk) {
@@ -279,9 +284,15 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
     BLADE_CUDA_OK(cudaStreamWaitEvent(fk->side, fk->fork, 0));
   }
   auto run_pool = [&]() -> int {
+    StageTimer timer(4, pstream);   // stage 4 = everything on the side stream: (v's copy +) gap pooling
+    if (v_later)
+      if (int e = prep_impl(q, k, v, src_row, ws + w.q_r, ws + w.k_r, ws + w.v_r, nullptr, nullptr, nullptr, nullptr,
+                            cfg->block_size, cfg->sample_gap, nullptr, 0, 1, pstream, nullptr, cfg->token_row, cfg->peers,
+                            4, -1))
+        return e;
     return prep_impl(q, k, v, src_row, rearr ? ws + w.q_r : nullptr, rearr ? ws + w.k_r : nullptr,
                      v_copy ? ws + w.v_r : nullptr, nullptr, nullptr, ws + w.k_pool, ws + w.v_pool, cfg->block_size,
-                     cfg->sample_gap, nullptr, 0, 2, pstream);
+                     cfg->sample_gap, nullptr, 0, 2, pstream, nullptr, nullptr, nullptr, 7, -1);
   };
   if (np && fork_mode != 1)
     if (int e = run_pool()) return e;

@@ -62,7 +62,8 @@ struct PrepNorm {
 int prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* src_row, void* q_r,
               void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool, int32_t block_size,
               int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row, int parts, cudaStream_t stream,
-              const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr, const BladePeers* peers = nullptr);
+              const PrepNorm* norm = nullptr, const int32_t* tok_row = nullptr, const BladePeers* peers = nullptr,
+              int tmask = 7 /* bit t: tensor t of (q, k, v) */, int stage = -2 /* profile-event stage override */);
 int score_select_impl(const float* q_mean, const float* k_mean, float* scores_opt, int64_t B, int64_t H, int64_t nb,
                       int64_t D, const BladeAsaConfig* cfg, int32_t* idx, int32_t* cnt, uint8_t* mask_opt,
                       cudaStream_t stream, bool pdl);

@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
                                                          const uint16_t* __restrict__ wk, int norm_kind,
                                                          const int32_t* __restrict__ tok_row,
                                                          const uint16_t* __restrict__ bq, const uint16_t* __restrict__ bk,
-                                                         float norm_eps, const __grid_constant__ PeerSrc peer) {
+                                                         float norm_eps, const __grid_constant__ PeerSrc peer,
+                                                         int tmask /* bit t: process tensor t of (q, k, v) */) {
   constexpr int LPR = D / 8;        // lanes per row (16-byte chunks)
   constexpr int RPW = 32 / LPR;     // rows per warp-wide load
   constexpr int RPP = 8 * RPW;      // rows per pass of the 8 warps
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
     const uint16_t* src = t == 0 ? q : (t == 1 ? k : v);
     const Strides3 st = t == 0 ? sq : (t == 1 ? sk : sv);
     uint16_t* dst = t == 0 ? q_r : (t == 1 ? k_r : v_r);
+    if (!((tmask >> t) & 1)) continue;                // this launch handles a subset of (q, k, v)
     if (t == 2 && !(COPY && dst != nullptr)) break;  // V is only needed for the copy
     const uint16_t* base = src + b * st.b + h * st.h;
     for (int p0 = 0; p0 < passes; p0 += 8) {
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(256, (ROPE || NORM) ? 3 : 0) prep_block_kernel
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) s += red[t][j][d];
     float* dstm = t == 0 ? q_mean : k_mean;
-    if (dstm) dstm[((static_cast<int64_t>(b) * H + h) * nb + blk) * D + d] = s / static_cast<float>(block);
+    if (dstm && ((tmask >> t) & 1)) dstm[((static_cast<int64_t>(b) * H + h) * nb + blk) * D + d] = s / static_cast<float>(block);
   }
 }
 
@@ -901,7 +903,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
                      void* k_r, void* v_r, float* q_mean, float* k_mean, void* k_pool, void* v_pool,
                      int32_t block_size, int32_t sample_gap, const float* rope_cos_sin, int32_t rope_first_row,
                      int parts, cudaStream_t stream, const PrepNorm* norm, const int32_t* tok_row,
-                     const BladePeers* peers) {
+                     const BladePeers* peers, int tmask, int stage) {
   if (int e = check_tensor16(q, "q")) return e;
   if (int e = check_tensor16(k, "k")) return e;
   if (int e = check_tensor16(v, "v")) return e;
@@ -945,14 +947,14 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   const bool bf = q->dtype == BLADE_BF16;
   Strides3 sq{q->stride[0], q->stride[1], q->stride[2]}, sk{k->stride[0], k->stride[1], k->stride[2]},
       sv{v->stride[0], v->stride[1], v->stride[2]};
-  StageTimer timer(parts == 2 ? 4 : 0, stream);
+  StageTimer timer(stage != -2 ? stage : (parts == 2 ? 4 : 0), stream);
   const uint16_t *qp = static_cast<const uint16_t*>(q->ptr), *kp = static_cast<const uint16_t*>(k->ptr),
                  *vp = static_cast<const uint16_t*>(v->ptr);
   const float* rstd = nullptr;
   const uint16_t *wq = nullptr, *wk = nullptr, *bq = nullptr, *bk = nullptr;
   int norm_kind = 0;
   float norm_eps = 0.f;
-  if (norm && norm->kind != 0 && (parts & 1)) {
+  if (norm && norm->kind != 0 && (parts & 1) && (tmask & 3)) {
     BLADE_REQUIRE(norm->kind >= 1 && norm->kind <= 3, BLADE_ERR_ARG, "qk_norm kind %d not in {1,2,3}", norm->kind);
     BLADE_REQUIRE(copy, BLADE_ERR_ARG, "qk_norm needs the q_r/k_r/v_r outputs");
     BLADE_REQUIRE(norm->q_weight && norm->k_weight && (norm->kind == 3 || norm->rstd || norm->rstd_ext), BLADE_ERR_ARG,
@@ -978,7 +980,7 @@ int blade::prep_impl(const BladeTensor* q, const BladeTensor* k, const BladeTens
   prep_block_kernel<DD, BF, CP, RP, NM, PE><<<grid, 256, 0, stream>>>(                                                \
       qp, kp, vp, sq, sk, sv, src_row, static_cast<uint16_t*>(q_r), static_cast<uint16_t*>(k_r),                      \
       static_cast<uint16_t*>(v_r), q_mean, k_mean, static_cast<int>(S), static_cast<int>(H), nb, block_size,          \
-      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps, psrc)
+      rope_cos_sin, rope_first_row, rstd, wq, wk, norm_kind, tok_row, bq, bk, norm_eps, psrc, tmask)
 #define LAUNCH_PREP(DD, BF, CP, RP, NM)                                                                               \
   do {                                                                                                                \
     if (CP && psrc.rows) LAUNCH_PREP_P(DD, BF, CP, RP, NM, (CP)); else LAUNCH_PREP_P(DD, BF, CP, RP, NM, false);      \
