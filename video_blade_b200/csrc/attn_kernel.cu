@@ -71,7 +71,12 @@ constexpr float kLn2 = 0.69314718055994530942f;
 #define BLADE_SOLO_DEN 2
 #endif
 constexpr int kItemSlots = 4;          // depth of the per-CTA item queue
-constexpr int kSchedBytes = 256;       // head of the attention workspace: the global item counter
+constexpr int kSchedBytes = 2048;      // head of the attention workspace: the global item counter + the arrival counters
+                                       // of the query tiles whose KV list is split across two CTAs (ints 16 ..)
+constexpr int kMaxSplitTiles = 496;    // (kSchedBytes / 4 - 16)
+constexpr int kSplitDone = 1 << 16;    // arrival counter of a split tile: low bits = halves that claimed, this bit = the first half's dump is complete
+template <int D>
+constexpr size_t kSplitSlotBytes = static_cast<size_t>(D) * 768 + 2048;  // per split tile, see the softmax warps
 
 template <int D>
 struct SmemLayout {
@@ -95,6 +100,7 @@ struct Misc {
   // work queue: the producer warp claims items (atomic counter) and publishes (item, cnt0, cnt1) here
   int4 items[kItemSlots];
   uint64_t item_full[kItemSlots], item_empty[kItemSlots];
+  int split_old;  // cross-CTA split: the arrival order of this half (broadcast from one thread to its warpgroup)
 };
 static_assert(sizeof(Misc) <= 2048, "misc smem region overflow");
 
@@ -111,7 +117,10 @@ struct AttnParams {
   int n_pool, n_pool_tiles;
   int num_items, pairs_per_head;
   int num_pair_items;      // items [0, num_pair_items) are tile pairs, the rest are solo tiles (two per pair id)
-  int num_solo_pairs;      // pair ids [0, num_solo_pairs) run as solo tiles
+  int num_solo_pairs;      // solo tiles: two items per pair id
+  int num_split_pairs;     // the LAST claims: tiles whose KV list is split across two CTAs (four items per pair id)
+  uint8_t* split_ws;       // per split tile: parked pooled tile, two fp32 partial accumulators, (m, l), lse2
+  int* split_cnt;          // arrival counters of the split tiles (zeroed with the item counter)
   int* sched;              // global item counter (zeroed before the launch); null = static round-robin
   float scale_log2;        // softmax_scale * log2(e)
   float log_gap_r;         // round_t(log(round_t(gap)))            (W:353-354)
@@ -188,6 +197,8 @@ struct Item {
   int bh;
   int qb[2], pt[2], off[2], ns[2];
   bool merge;  // solo item with work on both streams: warpgroup 0 folds stream 1's accumulator into its own
+  bool split;  // one HALF of a query tile's KV sequence (the other half runs on another CTA); slot / half say which
+  int slot, half;
 };
 // The per-row block counts are the only global-memory input of the decode; every role requests the NEXT item's
 // counts at the top of the current item (item_counts) and turns them into an Item one iteration later (make_item),
@@ -218,8 +229,17 @@ struct MultiMaps {
   CUtensorMap k[3], v[3];  // K / V mean-pooled by 2, 4, 8 (box rows 64, 32, 16)
 };
 
-__device__ __forceinline__ int pair_id_of(const AttnParams& p, int item) {
-  const int c = item < p.num_pair_items ? item : p.num_pair_items + ((item - p.num_pair_items) >> 1);
+// Item classes in claim order: [0, npi) tile pairs | [npi, npi + 2 nsolo) solo tiles | [.., + 4 nsplit) HALF tiles --
+// a query tile whose KV sequence is split across two CTAs, so that the last claims of a launch are quarter-length and
+// the tail of the persistent schedule is flat (3 heads on 148 CTAs = 2.59 rounds of pairs used to cost 3.1).
+// kind: 0 pair, 1 solo, 2 half; c = claim index of the pair slot; sub = which tile / half of it.
+__device__ __forceinline__ void classify(const AttnParams& p, int item, int& kind, int& c, int& sub) {
+  const int s0 = p.num_pair_items, s1 = s0 + 2 * p.num_solo_pairs;
+  if (item < s0) { kind = 0; c = item; sub = 0; }
+  else if (item < s1) { kind = 1; c = s0 + ((item - s0) >> 1); sub = (item - s0) & 1; }
+  else { kind = 2; c = s0 + p.num_solo_pairs + ((item - s1) >> 2); sub = (item - s1) & 3; }
+}
+__device__ __forceinline__ int pair_id_of(const AttnParams& p, int c) {
   const int bh_n = p.B * p.H, pph = p.pairs_per_head;
   if (pph == 1) return c;
   if (c < bh_n) return c * pph;
@@ -230,9 +250,11 @@ __device__ __forceinline__ int tile_of(const AttnParams& p, int pair, int t) { r
 __device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& c0, int& c1) {
   c0 = c1 = 0;
   if (item >= p.num_items) return;
-  if (item < p.num_pair_items) {
-    const int pid = pair_id_of(p, item);
-    const int bh = pid / p.pairs_per_head, pair = pid % p.pairs_per_head;
+  int kind, c, sub;
+  classify(p, item, kind, c, sub);
+  const int pid = pair_id_of(p, c);
+  const int bh = pid / p.pairs_per_head, pair = pid % p.pairs_per_head;
+  if (kind == 0) {
     if (p.cnt4) {  // multi-level: tile counts from the per-level entry counts
       const int4* row4 = p.cnt4 + static_cast<int64_t>(bh) * p.nq;
       c0 = multi_tiles(__ldg(row4 + tile_of(p, pair, 0)));
@@ -243,20 +265,21 @@ __device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& 
     c0 = __ldg(row + tile_of(p, pair, 0));
     if (2 * pair + 1 < p.nq) c1 = __ldg(row + tile_of(p, pair, 1));
   } else {
-    const int s = item - p.num_pair_items;
-    const int pid = pair_id_of(p, item);
-    const int bh = pid / p.pairs_per_head;
-    const int qb = tile_of(p, pid % p.pairs_per_head, s & 1);
+    const int qb = tile_of(p, pair, kind == 1 ? sub : (sub >> 1));
     if (qb >= 0) c0 = c1 = __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
   }
 }
 __device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0, int c1) {
   Item it;
   const int npt = p.n_pool_tiles;
-  if (item < p.num_pair_items) {
-    const int pid = pair_id_of(p, item);
-    it.bh = pid / p.pairs_per_head;
-    const int pair = pid % p.pairs_per_head;
+  int kind, cl, sub;
+  classify(p, item, kind, cl, sub);
+  const int pid = pair_id_of(p, cl);
+  it.bh = pid / p.pairs_per_head;
+  const int pair = pid % p.pairs_per_head;
+  it.split = false;
+  it.slot = it.half = 0;
+  if (kind == 0) {
     it.merge = false;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -268,27 +291,38 @@ __device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0,
       it.ns[t] = valid ? (t ? c1 : c0) : 0;
     }
   } else {
-    const int s = item - p.num_pair_items;
-    const int pid = pair_id_of(p, item);
-    it.bh = pid / p.pairs_per_head;
-    const int qbr = tile_of(p, pid % p.pairs_per_head, s & 1);
-    const bool valid = qbr >= 0;
+    const int qbr = tile_of(p, pair, kind == 1 ? sub : (sub >> 1));
+    // a list of fewer than 4 entries is not worth a second CTA: half 0 runs it as an ordinary solo tile, half 1 is empty
+    const bool halves = kind == 2 && c0 >= 4;
+    const bool valid = qbr >= 0 && !(kind == 2 && !halves && (sub & 1));
     const int qb = valid ? qbr : p.nq;
     const int c = valid ? c0 : 0;
-    // balance pooled + a  against  c - a tiles
-    int a = c;
-    if (c >= 2) {
-      a = (c - npt) / 2;
-      a = a < 1 ? 1 : (a > c - 1 ? c - 1 : a);
+    // my share of the tile: [lo, lo + n) of its list, and the pooled tiles if I own them
+    int lo = 0, n = c, mypt = valid ? npt : 0;
+    if (halves && valid) {
+      it.split = true;
+      it.half = sub & 1;
+      it.slot = (item - p.num_pair_items - 2 * p.num_solo_pairs) >> 1;
+      // half 0 = pooled tiles + entries [0, ca); half 1 = entries [ca, c); both halves keep >= 2 entries, so each has
+      // work on both streams (it.merge) -- the epilogue's half protocol relies on that
+      int ca = (c - npt) / 2;
+      ca = ca < 2 ? 2 : (ca > c - 2 ? c - 2 : ca);
+      if (it.half) { lo = ca; n = c - ca; mypt = 0; } else { n = ca; }
+    }
+    // two streams: balance pooled + a  against  n - a tiles
+    int a = n;
+    if (n >= 2) {
+      a = (n - mypt) / 2;
+      a = a < 1 ? 1 : (a > n - 1 ? n - 1 : a);
     }
     it.qb[0] = it.qb[1] = qb;
-    it.pt[0] = valid ? npt : 0;
+    it.pt[0] = mypt;
     it.pt[1] = 0;
-    it.off[0] = 0;
+    it.off[0] = lo;
     it.ns[0] = a;
-    it.off[1] = a;
-    it.ns[1] = c - a;
-    it.merge = c - a > 0;
+    it.off[1] = lo + a;
+    it.ns[1] = n - a;
+    it.merge = n - a > 0;
   }
   return it;
 }
@@ -615,6 +649,11 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
       // kernel's masked loads (K9:108-119,155-178); only partly filled pooled tiles are masked (per tile, below)
       const int sparse_tail = (!MULTI && last_kb == p.nk - 1) ? seq_tail : kBlockN;
       float lse2 = 0.f;
+      // half tiles (KV sequence split across two CTAs) keep their shared state in a per-tile slot of the workspace:
+      // [D/8][128] parked pooled tile | [D][128] fp32 partial of the half that finishes first | [128] (m, l) | [128] lse2
+      // (pointers formed where they are used: nothing extra stays live across the tile loops)
+      auto slot_ptr = [&]() { return p.split_ws + static_cast<size_t>(it.slot) * kSplitSlotBytes<D>; };
+      auto park_ptr = [&]() { return it.split ? reinterpret_cast<uint4*>(slot_ptr()) : park; };
       if (wq == 0 && sparse_tail > 0) TRACE(t, 7, g);  // item decoded (both dependent loads done)
 
       for (int phase = (my_pt ? 0 : 1); phase < 2; ++phase) {
@@ -734,6 +773,7 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
           tc_fence_after();
           const float inv_l = 1.0f / l;
           lse2 = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
+          uint4* const park_cur = park_ptr();
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
             uint32_t o[32];
@@ -746,7 +786,7 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
               w.y = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
               w.z = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
               w.w = pack_t<IS_BF16>(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
-              park[(c * 4 + u) * kBlockM + row_in_tile] = w;
+              park_cur[(c * 4 + u) * kBlockM + row_in_tile] = w;
             }
           }
         } else {
@@ -755,21 +795,49 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
           // round trip instead of a dependent one per 8 columns (which cost ~10 us per item).
           const int r = qb * kBlockM + row_in_tile;
           const bool store = r < p.S;
+          // ---- half tile: this CTA ran ONE HALF of the query tile's KV sequence (always a solo item with work on both
+          // streams).  One atomic per half decides the roles.  The half that finishes FIRST (role 1) writes its
+          // normalised accumulator (both streams folded) and (m, l) into the tile's slot and raises the slot's flag; the
+          // half that finishes SECOND (role 2) waits for that flag -- the partner is past its last MMA and only has its
+          // dump left, a bounded few-microsecond wait -- folds the partner's partial in as a third stream and runs the
+          // ordinary epilogue (pooled merge, inverse permutation, row store).
+          int role = 0;
+          float m2 = -INFINITY, l2 = 0.f, f0 = 0.f, f1 = 0.f;
+          uint8_t* const sslot = it.split ? slot_ptr() : nullptr;
+          const uint4* const park_cur = it.split ? reinterpret_cast<const uint4*>(sslot) : park;
+          if (it.split) {
+            mbar_wait(&mz->o_full[t], (g - 1) & 1);   // my own work is done before I claim (keeps role 2's wait short)
+            if (row_in_tile == 0) mz->split_old = atomicAdd(p.split_cnt + it.slot, 1);
+            named_bar_sync<3, kSoftmaxThreads>();
+            role = *reinterpret_cast<volatile int*>(&mz->split_old) == 0 ? 1 : 2;
+            if (role == 2) {
+              if (lane == 0) {
+                uint32_t polls = 0;
+                while ((*reinterpret_cast<volatile int*>(p.split_cnt + it.slot) & kSplitDone) == 0) {
+                  __nanosleep(64);
+                  if (++polls > (1u << 24)) __trap();
+                }
+              }
+              __syncwarp();
+              __threadfence();
+              const float2 mlp = __ldcg(reinterpret_cast<const float2*>(sslot + D * 768) + row_in_tile);
+              m2 = mlp.x;
+              l2 = mlp.y;
+              if (POOLED && it.half == 1) lse2 = __ldcg(reinterpret_cast<const float*>(sslot + D * 768 + 1024) + row_in_tile);
+            }
+          }
           uint4 parked[D / 8];
           if (POOLED) {  // compile-time: a runtime predicate here sends the array through local memory
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i) parked[i] = park[i * kBlockM + row_in_tile];
+            for (int i = 0; i < D / 8; ++i) parked[i] = __ldcg(park_cur + i * kBlockM + row_in_tile);
           }
           int dst = r;
           if (store && p.dst_row) dst = __ldg(p.dst_row + r);
           // (m, l) are final once the last tile's exponentials are summed, i.e. BEFORE its PV retires: the merge
           // weights and the row pointers are computed under the o_full wait (solo items redo them after the fold)
           float w0, w1 = 0.f, lse, alpha = 1.f, oma = 0.f;
-          auto weights = [&](float a0) {
-            const float inv_l = 1.0f / l;
+          auto merge_weights = [&]() {
             lse = (m + log2f(l)) * kLn2;  // natural-log LSE of the scaled scores
-            w0 = a0 * inv_l;
-            w1 *= inv_l;
             if (POOLED) {
               if (p.exact_merge) {
                 // W:351-370 op by op, every intermediate rounded to the tensor dtype (lse already is, W:309)
@@ -785,6 +853,12 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
                 oma = 1.0f - alpha;
               }
             }
+          };
+          auto weights = [&](float a0) {
+            const float inv_l = 1.0f / l;
+            w0 = a0 * inv_l;
+            w1 *= inv_l;
+            merge_weights();
           };
           if (!it.merge) weights(1.f);
           uint16_t* orow = nullptr;
@@ -818,9 +892,25 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
             l = a0 * l + w1 * ml1.y;
             m = mm;
             weights(a0);
+            if (role == 2) {
+              // the two halves' normalised partials X0, X1 combine as X0 * f0 + X1 * f1 with everything evaluated in HALF
+              // order (not arrival order), so the result does not depend on which CTA finished first
+              const float mA = it.half ? m2 : m, lA = it.half ? l2 : l, mB = it.half ? m : m2, lB = it.half ? l : l2;
+              const float mm2 = fmaxf(mA, mB);
+              const float sA = (mA == -INFINITY) ? 0.f : ex2_approx(mA - mm2) * lA;
+              const float sB = (mB == -INFINITY) ? 0.f : ex2_approx(mB - mm2) * lB;
+              l = sA + sB;
+              m = mm2;
+              const float inv_l = 1.0f / l;
+              f0 = sA * inv_l;
+              f1 = sB * inv_l;
+              merge_weights();
+            }
           }
           const uint32_t alpha2 = pack_t<IS_BF16>(alpha, alpha), oma2 = pack_t<IS_BF16>(oma, oma);
-          if (store && p.lse) p.lse[static_cast<int64_t>(bh) * p.S + r] = lse;
+          if (store && p.lse && role != 1) p.lse[static_cast<int64_t>(bh) * p.S + r] = lse;
+          // role 1's dump / role 2's third stream: fp32 [D][128] after the slot's parked pooled tile
+          float* const part = reinterpret_cast<float*>(sslot + D * 256) + row_in_tile;
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
             uint32_t(&o)[32] = ob[c & 1];
@@ -837,6 +927,21 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * w0);
             }
             if (c + 1 < D / 32) tmem_ld32(tO + (c + 1) * 32, ob[(c + 1) & 1]);
+            if (role == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) __stcg(part + (c * 32 + i) * kBlockM, __uint_as_float(o[i]));
+              continue;
+            }
+            if (role == 2) {
+              float o2[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o2[i] = __ldcg(part + (c * 32 + i) * kBlockM);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x0 = it.half ? o2[i] : __uint_as_float(o[i]), x1 = it.half ? __uint_as_float(o[i]) : o2[i];
+                o[i] = __float_as_uint(fmaf(x1, f1, x0 * f0));
+              }
+            }
             uint4 wq4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -872,6 +977,14 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
           if (it.merge) {
             tc_fence_before();
             named_bar_arrive<2, 2 * kSoftmaxThreads>();
+          }
+          if (role == 1) {
+            // publish: (m, l) of this half (+ the pooled branch's lse if it ran here), then the flag
+            __stcg(reinterpret_cast<float2*>(sslot + D * 768) + row_in_tile, make_float2(m, l));
+            if (POOLED && it.half == 0) __stcg(reinterpret_cast<float*>(sslot + D * 768 + 1024) + row_in_tile, lse2);
+            __threadfence();
+            named_bar_sync<3, kSoftmaxThreads>();
+            if (row_in_tile == 0) atomicOr(p.split_cnt + it.slot, kSplitDone);
           }
           if (wq == 0) TRACE(t, 6, g - 1);
         }
@@ -1006,9 +1119,15 @@ static int device_sm_count() {
 }
 
 // attention workspace: [0, 256) the item counter, then per CTA and stream one parked pooled-branch tile
+// attention workspace: [0, kSchedBytes) item counter + arrival counters | per CTA and stream one parked pooled-branch tile |
+// per half-split query tile (at most one per CTA) one slot of shared state
+static size_t attn_park_region(int64_t D) { return static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16; }
+static size_t attn_split_slot(int64_t D) { return D == 128 ? kSplitSlotBytes<128> : kSplitSlotBytes<64>; }
+static int attn_max_split_tiles() { return device_sm_count() < kMaxSplitTiles ? device_sm_count() : kMaxSplitTiles; }
 size_t attn_park_bytes(int64_t D) {
-  return kSchedBytes + static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16;
+  return kSchedBytes + attn_park_region(D) + static_cast<size_t>(attn_max_split_tiles()) * attn_split_slot(D);
 }
+size_t attn_sched_bytes() { return kSchedBytes; }
 
 static float round_host(float x, bool bf16) {
   return bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
@@ -1099,16 +1218,44 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
     // of the CTAs.
     static const bool no_split = getenv("BLADE_NO_SPLIT") && atoi(getenv("BLADE_NO_SPLIT")) != 0;
     const int np = (int)(B * H) * p.pairs_per_head, G = device_sm_count();
-    int split = 0;
+    // + the very last claims as HALF tiles (KV sequence of one query tile split across two CTAs, four items per pair):
+    // quarter-length items flatten the end of the schedule.  Needs the dynamic queue and the workspace (slots, arrival
+    // counters).  BLADE_NO_XSPLIT=1 disables (A/B).
+    static const bool no_xsplit = getenv("BLADE_NO_XSPLIT") && atoi(getenv("BLADE_NO_XSPLIT")) != 0;
+    // (not with 64x64 quadrant masks: there a half's entries can all be masked for a row, and 0 / 0 would enter the fold)
+    const bool can_x = !no_split && !no_xsplit && !multi && !sub64 && p.sched && workspace && ws_bytes >= attn_park_bytes(D);
+    static const int env_xs = getenv("BLADE_XSPLIT_PAIRS") ? atoi(getenv("BLADE_XSPLIT_PAIRS")) : -1;   // tuning knobs
+    static const int env_solo = getenv("BLADE_SOLO_PAIRS") ? atoi(getenv("BLADE_SOLO_PAIRS")) : -1;
+    int split = 0, xsplit = 0;
     if (!no_split && !multi) {  // multi-level rows are not split across the two streams
       const int r = np % G;
-      if (np < G) split = 2 * np <= G ? np : 0;
+      const int xmax = attn_max_split_tiles() / 2;   // pairs whose two tiles may be half-split
+      if (can_x) {
+        if (np >= G) {
+          // measured (tools/sweep_xsplit.sh, profiles/r02z_sweep_xsplit.log): G/8 pairs of half tiles behind G pairs of
+          // solo tiles is best or within noise of best for 12 and 3 Wan heads, uniform and non-uniform rows, and CogVideoX
+          const int want_x = env_xs >= 0 ? env_xs : G / 8, want_s = env_solo >= 0 ? env_solo : G;
+          xsplit = want_x < xmax ? want_x : xmax;
+          xsplit = xsplit < np ? xsplit : np;
+          split = want_s < np - xsplit ? want_s : np - xsplit;
+        } else if (2 * np <= G && 4 * np > G) {
+          split = np;                                   // one round of solo tiles already fills the machine
+        } else {
+          xsplit = np < xmax ? np : xmax;               // few pairs: quarter items
+          split = np - xsplit < G / 2 ? np - xsplit : G / 2;
+        }
+      } else if (np < G) split = 2 * np <= G ? np : 0;
       else if (p.sched) split = (G * BLADE_SOLO_NUM / BLADE_SOLO_DEN) < np ? G * BLADE_SOLO_NUM / BLADE_SOLO_DEN : np;
       else split = (r > 0 && 2 * r <= G) ? r : 0;
     }
-    p.num_pair_items = np - split;
+    p.num_pair_items = np - split - xsplit;
     p.num_solo_pairs = split;
-    p.num_items = p.num_pair_items + 2 * split;
+    p.num_split_pairs = xsplit;
+    p.num_items = p.num_pair_items + 2 * split + 4 * xsplit;
+    if (xsplit) {
+      p.split_cnt = static_cast<int*>(workspace) + 16;
+      p.split_ws = static_cast<uint8_t*>(workspace) + kSchedBytes + attn_park_region(D);
+    }
   }
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.gap = (float)sample_gap;
@@ -1142,7 +1289,7 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
 #endif
 
   const int grid = p.num_items < device_sm_count() ? p.num_items : device_sm_count();
-  if (p.sched && !sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, sizeof(int), stream));
+  if (p.sched && !sched_prezeroed) BLADE_CUDA_OK(cudaMemsetAsync(p.sched, 0, kSchedBytes, stream));
   StageTimer timer(3, stream);
   if (multi) {
     BLADE_REQUIRE(!pooled && !sub64 && multi->cnt4, BLADE_ERR_ARG, "multi-level attention: no pooled branch / block 64");

@@ -259,7 +259,7 @@ extern "C" int blade_asa_forward(const BladeTensor* q, const BladeTensor* k, con
 
   // the attention kernel's item counter (head of its workspace) is zeroed here, ahead of the mask kernels, so the
   // memset is not on the path between the selection and the attention launch
-  BLADE_CUDA_OK(cudaMemsetAsync(ws + w.park, 0, sizeof(int), stream));
+  BLADE_CUDA_OK(cudaMemsetAsync(ws + w.park, 0, attn_sched_bytes(), stream));
   const bool need_means = scores_in == nullptr && !sampled;
   // gather / rotate / block means on the caller's stream ...
   // q and k first (the score + selection chain only needs their block means); v's copy runs on the side stream in front

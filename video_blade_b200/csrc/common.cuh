@@ -78,6 +78,7 @@ struct MultiLevelArgs {
   const int32_t* cnt4;  // device int32 [B,H,nq,4]: list entries of level 1, 2, 4, 8 (list sorted by level, then block id)
 };
 size_t attn_park_bytes(int64_t D);
+size_t attn_sched_bytes();  // head of the attention workspace that must be zero at launch (item + arrival counters)
 void attn_sched_prezeroed();
 void attn_next_sub64();
 int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v, const int32_t* idx,
