@@ -7,20 +7,6 @@
 #include "../../video_blade_b200/csrc/ptx.cuh"
 using namespace blade;
 
-__device__ __forceinline__ void ex2_poly_x2(uint64_t x, float& p0, float& p1) {
-  const uint64_t xc = pack_f32x2(fmaxf(lo_f32(x), -125.f), fmaxf(hi_f32(x), -125.f));
-  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
-  const uint64_t t = add_f32x2(xc, magic);
-  const uint64_t fl = add_f32x2(t, nmagic);
-  const uint64_t f = fma_f32x2(fl, pack_f32x2(-1.f, -1.f), xc);
-  uint64_t p = fma_f32x2(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f,
-                         pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
-  p = fma_f32x2(p, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
-  p = fma_f32x2(p, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
-  p0 = __uint_as_float(static_cast<uint32_t>(p) + (static_cast<uint32_t>(t) << 23));
-  p1 = __uint_as_float(static_cast<uint32_t>(p >> 32) + (static_cast<uint32_t>(t >> 32) << 23));
-}
-
 // POLY = number of pairs out of every 8 pairs that use the polynomial
 template <int POLY>
 __global__ void __launch_bounds__(256) k(uint32_t* out, float seed, int tiles, long long* cyc) {

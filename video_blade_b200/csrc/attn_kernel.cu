@@ -70,6 +70,12 @@ constexpr float kLn2 = 0.69314718055994530942f;
 #define BLADE_SOLO_NUM 1        // dynamic queue: the last G * NUM / DEN pairs run as solo tiles
 #define BLADE_SOLO_DEN 2
 #endif
+// of every 8 (score pair) exponentials, this many run as a Cody-Waite polynomial on the FMA pipe instead of MUFU.EX2
+// (tools/microbench/softmax_loop.cu: 1 of 8 shortens the softmax loop by 7-8 %, 2 of 8 is break-even, more loses)
+#ifndef BLADE_POLY_PAIRS
+#define BLADE_POLY_PAIRS 0
+#endif
+constexpr int kPolyPairs = BLADE_POLY_PAIRS;
 constexpr int kItemSlots = 4;          // depth of the per-CTA item queue
 constexpr int kSchedBytes = 2048;      // head of the attention workspace: the global item counter + the arrival counters
                                        // of the query tiles whose KV list is split across two CTAs (ints 16 ..)
@@ -723,6 +729,8 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
           }
           if (wq == 0) TRACE(t, 2, g);
           const float neg_m = ((m == -INFINITY) ? 0.f : -m) + bias;  // all-masked so far: exp2(-inf - 0) = 0, never NaN
+          // polynomial exponentials only on tiles without masked (-inf) scores: the polynomial clamps instead of returning 0
+          const bool unmasked = kPolyPairs > 0 && valid == kBlockN && cmask == 3u;
           // packed fp32x2 math: x = s * scale - m and the row-sum accumulation take one issue slot per PAIR
           const uint64_t sl2_2 = pack_f32x2(sl2, sl2), negm_2 = pack_f32x2(neg_m, neg_m);
           uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};  // four independent packed sum chains
@@ -732,8 +740,13 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const uint64_t x = fma_f32x2(pack_u32x2(s[c][2 * i], s[c][2 * i + 1]), sl2_2, negm_2);
-              const float p0 = ex2_approx(lo_f32(x));
-              const float p1 = ex2_approx(hi_f32(x));
+              float p0, p1;
+              if (kPolyPairs > 0 && (i & 7) < kPolyPairs && unmasked) {
+                ex2_poly_x2(x, p0, p1);   // this pair on the FMA pipe (MUFU is the softmax's critical resource)
+              } else {
+                p0 = ex2_approx(lo_f32(x));
+                p1 = ex2_approx(hi_f32(x));
+              }
               ls2[i & 3] = add_f32x2(ls2[i & 3], pack_f32x2(p0, p1));
               pk[i] = pack_t<IS_BF16>(p0, p1);
             }
@@ -1109,7 +1122,7 @@ static thread_local int g_sub64_next = 0;  // set by blade_block_sparse_attn64_f
 void attn_next_sub64() { g_sub64_next = 1; }
 
 
-static int device_sm_count() {
+int device_sm_count() {
   static int n[64] = {0};  // per device: one process may drive several GPUs
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1118,7 +1131,6 @@ static int device_sm_count() {
   return c;
 }
 
-// attention workspace: [0, 256) the item counter, then per CTA and stream one parked pooled-branch tile
 // attention workspace: [0, kSchedBytes) item counter + arrival counters | per CTA and stream one parked pooled-branch tile |
 // per half-split query tile (at most one per CTA) one slot of shared state
 static size_t attn_park_region(int64_t D) { return static_cast<size_t>(device_sm_count()) * 2 * (D / 8) * kBlockM * 16; }

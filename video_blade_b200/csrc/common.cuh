@@ -77,6 +77,7 @@ struct MultiLevelArgs {
   const BladeTensor* v[3];
   const int32_t* cnt4;  // device int32 [B,H,nq,4]: list entries of level 1, 2, 4, 8 (list sorted by level, then block id)
 };
+int device_sm_count();  // SMs of the current device (cached per device)
 size_t attn_park_bytes(int64_t D);
 size_t attn_sched_bytes();  // head of the attention workspace that must be zero at launch (item + arrival counters)
 void attn_sched_prezeroed();

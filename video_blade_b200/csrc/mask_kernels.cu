@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const uint16_t* __restrict__ 
 // dynamic smem: (16*(D+nb) + 64*(D+4)) floats
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreRows = 16;
-constexpr int kFusedRows = 16;  // rows per CTA of the fused score + selection kernel (8 was slower: every CTA streams all K means)
+constexpr int kFusedRows = 16;  // rows per CTA of the fused score + selection kernel at full size (8 was slower there: every CTA
+                                // streams all K means); few heads (one Ulysses rank) take 8 or 4 rows per CTA to fill the machine
 constexpr int kScoreChunk = 64;
 // Body shared by score_meanpool_kernel (R = 16 rows per CTA) and the fused score + selection kernel (R = 8: twice the
 // CTAs, one selection row per warp): leaves the CTA's R softmax rows in shared memory (srow, [R][nb]) and, if `scores` is given, writes them to global memory.
@@ -475,11 +476,12 @@ __device__ __forceinline__ void score_rows(const float* __restrict__ qm, const f
     }
   }
   __syncthreads();
-  // row softmax: two rows per warp
-  for (int rr = 0; rr < (R / 8); ++rr) {
-    const int r = warp * ((R / 8)) + rr;
+  // row softmax: R / 8 rows per warp (R < 8: one row on each of the first R warps)
+  constexpr int RPW = R >= 8 ? R / 8 : 1;
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = warp * RPW + rr;
     const int i = i0 + r;
-    if (i >= nb) break;
+    if (r >= R || i >= nb) break;
     float* row = srow + r * nb;
     float mx = -INFINITY;
     for (int j = lane; j < nb; j += 32) mx = fmaxf(mx, row[j]);
@@ -519,7 +521,7 @@ __device__ __forceinline__ int select_row_bitonic(const float* src, int nk, int 
 // energy-threshold selection + index list, one launch; the fp32 score map only goes to memory when the caller asks for
 // it.  Same arithmetic, bit for bit, as score_meanpool_kernel followed by select_bitonic_kernel<E> (the selection reads
 // the rows from shared memory instead of global).  dynamic smem: the score part + 8 warps * (N doubles + N ints).
-template <int D, int E>
+template <int D, int E, int R>
 __global__ void __launch_bounds__(256, 3) score_select_kernel(const float* __restrict__ qm, const float* __restrict__ km,
                                                            float* __restrict__ scores_opt, int nb, float scale, int lo,
                                                            int hi, float thr, int force_last, int rounding,
@@ -530,22 +532,23 @@ __global__ void __launch_bounds__(256, 3) score_select_kernel(const float* __res
   extern __shared__ __align__(16) float sm[];
   // programmatic dependent launch: everything above the first global read may overlap the producer's tail
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  score_rows<D, kFusedRows>(qm, km, scores_opt, nb, scale, sm);
+  score_rows<D, R>(qm, km, scores_opt, nb, scale, sm);
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* srow = sm + kFusedRows * D;
+  const float* srow = sm + R * D;
   // the selection scratch (8 warps x (N doubles + N ints) <= 24 KB) aliases the K-means chunk buffer (64 x (D+4) floats
   // >= 17 KB for D = 64, 33 KB for D = 128), dead once the scores are in srow; what does not fit follows the score region
-  const size_t srow_end = static_cast<size_t>(kFusedRows) * (D + nb);
+  const size_t srow_end = static_cast<size_t>(R) * (D + nb);
   double* sorted = reinterpret_cast<double*>(sm + ((srow_end + 1) & ~size_t(1))) + warp * 2 * N;
   int* flag = reinterpret_cast<int*>(sorted + N);
   const int64_t bh = blockIdx.y;
   int total = 0;
-  for (int rr = 0; rr < kFusedRows / 8; ++rr) {
-    const int r = warp * (kFusedRows / 8) + rr;
-    const int qi = blockIdx.x * kFusedRows + r;
-    if (qi >= nb) break;
+  constexpr int RPW = R >= 8 ? R / 8 : 1;
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = warp * RPW + rr;
+    const int qi = blockIdx.x * R + r;
+    if (r >= R || qi >= nb) break;
     const int64_t row = bh * nb + qi;
     const int base = select_row_bitonic<E>(srow + r * nb, nb, qi, nb, lo, hi, thr, force_last, rounding, sorted, flag,
                                            idx + row * nb, mask ? mask + row * nb : nullptr, nullptr, lane);
@@ -1049,7 +1052,13 @@ int blade::score_select_impl(const float* q_mean, const float* k_mean, float* sc
                              cudaStream_t stream, bool pdl) {
   if (nb > 256 || (D != 64 && D != 128)) return -1;
   const int E = nb <= 32 ? 1 : (nb <= 64 ? 2 : (nb <= 128 ? 4 : 8));
-  const size_t srow_end = ((static_cast<size_t>(kFusedRows) * (D + nb) + 1) & ~size_t(1)) * sizeof(float);
+  // rows per CTA: 16, or fewer when that leaves SMs without a CTA (the kernel's time is the latency of ONE CTA: with 3 Wan
+  // heads 16 rows per CTA is 48 CTAs of ~50 us each).  BLADE_FUSED_ROWS = 4 | 8 | 16 forces one (A/B).
+  static const int env_rows = getenv("BLADE_FUSED_ROWS") ? atoi(getenv("BLADE_FUSED_ROWS")) : 0;
+  int R = kFusedRows;
+  while (R > 8 && B * H * ceil_div(nb, R) < device_sm_count()) R >>= 1;   // measured: 3 Wan heads 44 / 30 / 32 us at 16 / 8 / 4
+  if (env_rows == 4 || env_rows == 8 || env_rows == 16) R = env_rows;
+  const size_t srow_end = ((static_cast<size_t>(R) * (D + nb) + 1) & ~size_t(1)) * sizeof(float);
   const size_t chunk_bytes = static_cast<size_t>(kScoreChunk) * (D + 4) * sizeof(float);
   const size_t sel_bytes = 8 * (2 * 32 * E) * sizeof(double);
   const size_t smem = srow_end + (chunk_bytes > sel_bytes ? chunk_bytes : sel_bytes) + 16;
@@ -1060,7 +1069,7 @@ int blade::score_select_impl(const float* q_mean, const float* k_mean, float* sc
   StageTimer t1(1, stream);   // the fused launch is reported as stage 1 (scores); stage 2 (select) collapses to ~0
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3(static_cast<unsigned>(ceil_div(nb, kFusedRows)), static_cast<unsigned>(B * H));
+  lc.gridDim = dim3(static_cast<unsigned>(ceil_div(nb, R)), static_cast<unsigned>(B * H));
   lc.blockDim = dim3(256);
   lc.dynamicSmemBytes = smem;
   lc.stream = stream;
@@ -1072,7 +1081,7 @@ int blade::score_select_impl(const float* q_mean, const float* k_mean, float* sc
   const int nbi = static_cast<int>(nb);
 #define LAUNCH_FUSED(DD, EE)                                                                                          \
   do {                                                                                                                \
-    auto kern = score_select_kernel<DD, EE>;                                                                          \
+    auto kern = R == 16 ? score_select_kernel<DD, EE, 16> : (R == 8 ? score_select_kernel<DD, EE, 8> : score_select_kernel<DD, EE, 4>); \
     if (smem > 48 * 1024)                                                                                             \
       BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     BLADE_CUDA_OK(cudaLaunchKernelEx(&lc, kern, q_mean, k_mean, scores_opt, nbi, scale, (int)cfg->min_retain,         \

@@ -253,6 +253,21 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ float lo_f32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
 __device__ __forceinline__ float hi_f32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+// two 2^x on the FMA/ALU pipes (ex2_poly on a packed pair): clamp at -125, magic-number rounding, degree-3 polynomial in
+// packed fp32x2, exponent spliced in with an integer shift-add.  x <= ~100; max relative error 7.7e-5.
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x, float& p0, float& p1) {
+  const uint64_t xc = pack_f32x2(fmaxf(lo_f32(x), -125.f), fmaxf(hi_f32(x), -125.f));
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t t = add_f32x2(xc, magic);
+  const uint64_t fl = add_f32x2(t, nmagic);
+  const uint64_t f = fma_f32x2(fl, pack_f32x2(-1.f, -1.f), xc);
+  uint64_t p = fma_f32x2(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f,
+                         pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+  p0 = __uint_as_float(static_cast<uint32_t>(p) + (static_cast<uint32_t>(t) << 23));
+  p1 = __uint_as_float(static_cast<uint32_t>(p >> 32) + (static_cast<uint32_t>(t >> 32) << 23));
+}
 
 // pack two fp32 into bf16x2: lo -> bits [0,16), hi -> bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
