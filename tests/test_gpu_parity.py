@@ -544,6 +544,50 @@ def test_many_items_per_cta_nonuniform_rows_vs_torch_fp32():
             _close(lse[b, h], torch.logsumexp(s, -1), 1e-5, 1e-4)
 
 
+def test_half_tile_items_vs_torch_fp32_and_run_to_run_identical():
+    """Half-tile items: the last claims of a launch are query tiles whose KV list is split across TWO CTAs; the half
+    that finishes second folds the other half's partial in (attn_kernel.cu, roles 1 / 2).  (a) 150 tile pairs on 148
+    CTAs (pairs, solo tiles and half tiles in one launch), rows keeping 1..30 of 100 blocks (lists shorter than 4
+    entries are not split), ragged last block, against fp32 torch attention; (b) 8 tile pairs (every tile is split),
+    pooled branch + bf16 merge against the oracle; both launched repeatedly: bit-identical outputs (the fold is
+    evaluated in half order, not arrival order)."""
+    eng = _engine(use_rearrange=False, sample_gap=30)
+    B, H, S, D, nb = 1, 3, 100 * 128 - 21, 128, 100
+    g = torch.Generator(device="cuda").manual_seed(17)
+    q, k, v = (torch.randn(B, S, H, D, device="cuda", generator=g).to(torch.bfloat16).transpose(1, 2) for _ in range(3))
+    score = torch.rand(B, H, nb, nb, device="cuda", generator=g)
+    counts = torch.randint(1, 31, (B, H, nb, 1), device="cuda", generator=g)
+    kth = torch.sort(score, dim=-1, descending=True).values.gather(-1, counts - 1)
+    mask = score >= kth
+    idx, cnt = eng.mask_to_index(mask)
+    out, lse = eng.block_sparse_attn(q, k, v, idx, cnt)
+    for h in range(H):
+        tok = mask[0, h].repeat_interleave(128, 0).repeat_interleave(128, 1)[:S, :S]
+        s_ = (q[0, h].float() @ k[0, h].float().T) / D ** 0.5
+        s_ = s_.masked_fill(~tok, float("-inf"))
+        _close(out[0, h], (torch.softmax(s_, -1) @ v[0, h].float()).to(torch.bfloat16))
+        _close(lse[0, h], torch.logsumexp(s_, -1), 1e-5, 1e-4)
+    kp, vp = eng.prep(q, k, v, rearrange=False, want_means=False, want_pool=True)[2]
+    first = eng.asa_attn(q, k, v, idx, cnt, kp, vp).clone()
+    for _ in range(5):
+        assert torch.equal(eng.asa_attn(q, k, v, idx, cnt, kp, vp), first)
+    # (b) every tile split, pooled branch and merge, against the CPU oracle
+    S2, H2 = 2048, 1
+    q2, k2, v2 = O.synth_qkv(1, H2, S2, D, seed=23)
+    nb2 = S2 // 128
+    m2 = torch.rand(1, H2, nb2, nb2, generator=torch.Generator().manual_seed(4)) < 0.6
+    m2[..., 0] = True
+    m2[0, 0, 5, :] = True
+    i2, c2 = O.mask_to_index_list(m2)
+    kp2, vp2 = O.simple_pooling(k2, 30), O.simple_pooling(v2, 30)
+    got = eng.asa_attn(q2.cuda(), k2.cuda(), v2.cuda(), i2.cuda(), c2.cuda(), kp2.cuda(), vp2.cuda())
+    wout, wlse = O.dense_masked_attention(q2, k2, v2, m2)
+    o2, l2 = O.standard_attn(q2, kp2, vp2)
+    _close(got, O.merge_lse(wout, wlse.unsqueeze(-1).to(q2.dtype), o2, l2.unsqueeze(-1).to(q2.dtype), 30))
+    for _ in range(5):
+        assert torch.equal(eng.asa_attn(q2.cuda(), k2.cuda(), v2.cuda(), i2.cuda(), c2.cuda(), kp2.cuda(), vp2.cuda()), got)
+
+
 # ------------------------------------------------------------------ the benchmarked sizes (BASELINE configs 2 and 4)
 def _full_size_layer(flavor, H, seed, structured):
     """Whole layer -- gather, estimator, selection, sparse branch, pooled branch, bf16 merge, inverse permute -- at the

@@ -75,10 +75,15 @@ struct EstMisc {
   uint32_t tmem_base;
 };
 
-template <int D, bool IS_BF16>
+// CS = cluster size along the query-tile axis (1 or 2).  The kernel is bound by L2 -> SM traffic (every CTA streams all
+// sampled keys of its head: 2 MB x 768 CTAs at Wan size), so with CS = 2 the two CTAs of a cluster -- two query tiles of
+// the SAME head -- share every key tile: each issues the TMA for one half of it (tmKh: 64-row boxes) with
+// .multicast::cluster to both, and a ring slot is released by BOTH issuers' tcgen05.commit (multicast to the two
+// k_empty barriers, count 2).
+template <int D, bool IS_BF16, int CS>
 __global__ void __launch_bounds__(192, 1)
 sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     float* __restrict__ scores, int nb, float scale_log2) {
+                     const __grid_constant__ CUtensorMap tmKh, float* __restrict__ scores, int nb, float scale_log2) {
   using L = EstSmem<D>;
   constexpr int kStages = L::kStages;
   constexpr int kTileBytes = L::kTileBytes;
@@ -98,7 +103,7 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(&mz->q_full, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&mz->k_full[s], 1);
-      mbar_init(&mz->k_empty[s], 1);
+      mbar_init(&mz->k_empty[s], CS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mz->s_full[i], 1);
@@ -109,8 +114,10 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 5) tmem_alloc<256>(&mz->tmem_base);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = mz->tmem_base;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
 
   if (warp == 4) {
     // ------------------------------ TMA producer
@@ -124,10 +131,17 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int jt = 0; jt < nkt; ++jt) {
       mbar_wait(&mz->k_empty[slot], ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&mz->k_full[slot], kTileBytes);
-        for (int dh = 0; dh < kSub; ++dh)
-          tma_load_4d(sK + slot * kTileBytes + dh * (kTileR * 128), &tmK, &mz->k_full[slot], dh * 64, jt * kTileR, h,
-                      b, kEvictLast);
+        mbar_arrive_expect_tx(&mz->k_full[slot], kTileBytes);   // my half + the peer's half
+        if (CS > 1) {
+          constexpr int kHalf = kTileR / CS;
+          for (int dh = 0; dh < kSub; ++dh)
+            tma_load_4d_mc(sK + slot * kTileBytes + dh * (kTileR * 128) + crank * (kHalf * 128), &tmKh, &mz->k_full[slot],
+                           dh * 64, jt * kTileR + crank * kHalf, h, b, static_cast<uint16_t>((1u << CS) - 1), kEvictLast);
+        } else {
+          for (int dh = 0; dh < kSub; ++dh)
+            tma_load_4d(sK + slot * kTileBytes + dh * (kTileR * 128), &tmK, &mz->k_full[slot], dh * 64, jt * kTileR, h,
+                        b, kEvictLast);
+        }
       }
       __syncwarp();
       if (++slot == kStages) {
@@ -154,7 +168,8 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t koff = static_cast<uint32_t>((k >> 2) * (kTileR * 128 / 16) + (k & 3) * 2);
           umma_ss(tmem_base + bsel * kTileR, adesc + koff, bdesc + koff, idesc, k > 0);
         }
-        tc_commit(&mz->k_empty[slot]);
+        if (CS > 1) tc_commit_mc(&mz->k_empty[slot], static_cast<uint16_t>((1u << CS) - 1));
+        else tc_commit(&mz->k_empty[slot]);
         tc_commit(&mz->s_full[bsel]);
       }
       __syncwarp();
@@ -242,6 +257,7 @@ sampled_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // nobody leaves while the peer may still multicast into this CTA
   if (warp == 5) tmem_dealloc<256>(tmem_base);
 }
 
@@ -281,21 +297,43 @@ extern "C" int blade_asa_scores_sampled(const void* q_s, const void* k_s, float*
   BLADE_REQUIRE(nb >= 1 && nb <= 256, BLADE_ERR_SHAPE, "sampled estimator supports nb <= 256 blocks (got %lld)", (long long)nb);
   BLADE_REQUIRE(dtype == BLADE_BF16 || dtype == BLADE_F16, BLADE_ERR_DTYPE, "dtype");
   const int64_t Ss = nb * kKeep;
-  CUtensorMap tmQ, tmK;
+  CUtensorMap tmQ, tmK, tmKh;
   if (int e = make_tmap(&tmQ, q_s, dtype, B, H, Ss, D, H * Ss * D, Ss * D, D)) return e;
   if (int e = make_tmap(&tmK, k_s, dtype, B, H, Ss, D, H * Ss * D, Ss * D, D)) return e;
+  if (int e = make_tmap(&tmKh, k_s, dtype, B, H, Ss, D, H * Ss * D, Ss * D, D, kTileR / 2)) return e;
   StageTimer timer(1, stream);
-  dim3 grid(static_cast<unsigned>(ceil_div(nb, 4)), static_cast<unsigned>(H), static_cast<unsigned>(B));
+  // BLADE_EST_CLUSTER=2: clusters of two query tiles of one head share the key tiles (TMA multicast).  Measured
+  // (profiles/r02z_estimator_cluster.txt): L2 reads halve (1.6 -> 0.85 GB) but the kernel does not get faster (0.240 vs
+  // 0.244 ms) -- every SM still ingests each full 32 KB tile, and the tile rate is set by the bytes the 4-stage ring keeps
+  // in flight against the L2 latency under load (128 KB / ~4 000 cycles), not by L2 bandwidth.  Default: no cluster.
+  static const int env_cs = getenv("BLADE_EST_CLUSTER") ? atoi(getenv("BLADE_EST_CLUSTER")) : 1;
+  const int cs = env_cs == 2 ? 2 : 1;
+  const unsigned qtiles = static_cast<unsigned>(ceil_div(nb, 4));
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(D))) * 1.44269504f;  // P:163 literal
-#define LAUNCH_EST(DD, BF)                                                                                          \
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((qtiles + cs - 1) / cs * cs, static_cast<unsigned>(H), static_cast<unsigned>(B));  // an odd last tile is padded
+  lc.blockDim = dim3(192);
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  const int nbi = static_cast<int>(nb);
+#define LAUNCH_EST(DD, BF, CSZ)                                                                                     \
   do {                                                                                                              \
-    auto kern = sampled_score_kernel<DD, BF>;                                                                       \
+    auto kern = sampled_score_kernel<DD, BF, CSZ>;                                                                  \
+    lc.dynamicSmemBytes = EstSmem<DD>::kTotal;                                                                      \
     BLADE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EstSmem<DD>::kTotal));    \
-    kern<<<grid, 192, EstSmem<DD>::kTotal, stream>>>(tmQ, tmK, scores, (int)nb, scale_log2);                        \
+    BLADE_CUDA_OK(cudaLaunchKernelEx(&lc, kern, tmQ, tmK, tmKh, scores, nbi, scale_log2));                          \
   } while (0)
+#define LAUNCH_EST_D(DD, BF) do { if (cs == 2) LAUNCH_EST(DD, BF, 2); else LAUNCH_EST(DD, BF, 1); } while (0)
   const bool bf = dtype == BLADE_BF16;
-  if (D == 128) { if (bf) LAUNCH_EST(128, true); else LAUNCH_EST(128, false); }
-  else          { if (bf) LAUNCH_EST(64, true); else LAUNCH_EST(64, false); }
+  if (D == 128) { if (bf) LAUNCH_EST_D(128, true); else LAUNCH_EST_D(128, false); }
+  else          { if (bf) LAUNCH_EST_D(64, true); else LAUNCH_EST_D(64, false); }
+#undef LAUNCH_EST_D
 #undef LAUNCH_EST
   BLADE_CUDA_OK(cudaGetLastError());
   return BLADE_OK;
