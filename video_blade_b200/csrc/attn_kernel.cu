@@ -492,11 +492,17 @@ __device__ __forceinline__ void attn_body(const CUtensorMap& tmQ, const CUtensor
           row = kb * kBlockN;
         }
         if (elect_one()) {
+#ifdef BLADE_DIAG_HALF_KV
+          // DIAGNOSTIC build only (wrong results): fetch half of every K/V tile -- is the kernel bound by L2 -> SM bytes?
+          mbar_arrive_expect_tx(&mz->kv_full[slot], kTileBytes / kSub);
+          tma_load_4d(sKV + slot * kTileBytes, map, &mz->kv_full[slot], 0, row, h, b, BLADE_KV_HINT);
+#else
           mbar_arrive_expect_tx(&mz->kv_full[slot], kTileBytes);
 #pragma unroll
           for (int dh = 0; dh < kSub; ++dh)
             tma_load_4d(sKV + slot * kTileBytes + dh * (kBlockN * 128), map, &mz->kv_full[slot], dh * 64, row, h, b,
                         BLADE_KV_HINT);
+#endif
         }
         __syncwarp();
         if (++slot == kStages) {

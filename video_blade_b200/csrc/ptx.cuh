@@ -245,6 +245,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
