@@ -343,6 +343,17 @@ int blade_probe_qk(const void* q_tile /*bf16 [128,D]*/, const void* k_tile /*bf1
 int blade_probe_pv(const float* p_tile /*[128,128]*/, const void* v_tile /*bf16 [128,D]*/,
                    float* o_out /*[128,D]*/, int32_t D, void* stream);
 
+/* ---- schedule replay (tests only, HOST code, no GPU needed) -------------------------------------
+ * The persistent attention kernel decodes its work items (tile pairs, solo tiles, half tiles) with integer code
+ * shared by host and device.  This entry point replays the decode of one launch on host block counts `cnt_host`
+ * (int32 [B,H,nq]) for a device with `sm_count` SMs and writes 12 ints per item to items_out:
+ *   item, bh, {qb, pooled_tiles, list_offset, list_entries} x 2 streams, merge, split (0 | 1 + 2*slot + half)
+ * (qb == nq: stream without a tile).  dynamic_queue / half_tiles select the scheduling variants of
+ * blade_asa_attn_fwd.  Returns BLADE_ERR_WORKSPACE (and *n_items_out) when max_items is too small. */
+int blade_debug_attn_schedule(int64_t B, int64_t H, int64_t nq, int32_t n_pool_tiles, int32_t sm_count,
+                              const int32_t* cnt_host, int32_t dynamic_queue, int32_t half_tiles,
+                              int32_t* items_out, int64_t max_items, int32_t* n_items_out);
+
 #ifdef __cplusplus
 }
 #endif

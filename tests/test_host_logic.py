@@ -48,3 +48,69 @@ def test_select_rounding_knob_reaches_the_c_config():
     assert AsaKnobs.wan().c_config(256).select_rounding == 0
     assert AsaKnobs.wan(select_rounding="bf16").c_config(256).select_rounding == 1
     assert AsaKnobs.cog(select_rounding="f16").c_config(139).select_rounding == 2
+
+
+def _replay_schedule(B, H, nq, npt, G, cnt, dynamic=True, half_tiles=True):
+    import ctypes as C
+    import numpy as np
+    from video_blade_b200 import _lib
+    lib = _lib.load()
+    cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+    cap = 4 * B * H * ((nq + 1) // 2) + 8
+    items = np.zeros((cap, 12), dtype=np.int32)
+    n = C.c_int32(0)
+    _lib.check(lib.blade_debug_attn_schedule(B, H, nq, npt, G, cnt.ctypes.data, int(dynamic), int(half_tiles),
+                                             items.ctypes.data, cap, C.byref(n)))
+    return items[:n.value]
+
+
+@pytest.mark.parametrize("B,H,nq,npt,G", [(1, 12, 256, 9, 148), (1, 3, 256, 9, 148), (1, 48, 139, 10, 148), (2, 5, 7, 3, 148),
+                                          (1, 1, 1, 1, 148), (1, 2, 33, 0, 148), (1, 1, 16, 1, 148), (3, 7, 64, 2, 132),
+                                          (1, 40, 64, 9, 148), (1, 1, 300, 2, 8)])
+@pytest.mark.parametrize("dynamic,half_tiles", [(True, True), (True, False), (False, False)])
+def test_attention_schedule_covers_every_tile_exactly_once(B, H, nq, npt, G, dynamic, half_tiles):
+    """Host replay of the persistent attention kernel's item decode (the same classify / make_item code the device roles
+    run, `blade_debug_attn_schedule`): for every (batch*head, query tile) the pooled tiles are run exactly once and the
+    slices [off, off + n) of the block list handed to streams / CTAs partition [0, count) -- for tile pairs, solo tiles
+    and half tiles, odd tile counts, short lists and fewer pairs than SMs."""
+    import numpy as np
+    rng = np.random.default_rng(B * 1000 + H * 10 + nq)
+    cnt = rng.integers(1, 45, size=(B, H, nq), dtype=np.int32)
+    cnt[..., : max(1, nq // 7)] = rng.integers(1, 5, size=(B, H, max(1, nq // 7)))     # lists too short to split
+    items = _replay_schedule(B, H, nq, npt, G, cnt, dynamic, half_tiles)
+    pooled = np.zeros((B * H, nq), dtype=np.int64)
+    cover = [[[] for _ in range(nq)] for _ in range(B * H)]
+    halves = {}
+    for row in items:
+        item, bh, merge, split = int(row[0]), int(row[1]), int(row[10]), int(row[11])
+        assert 0 <= bh < B * H
+        streams = [tuple(int(x) for x in row[2 + 4 * t: 6 + 4 * t]) for t in range(2)]     # (qb, pt, off, ns)
+        for t, (qb, pt, off, ns) in enumerate(streams):
+            assert 0 <= qb <= nq and pt in (0, npt) and off >= 0 and ns >= 0
+            if qb == nq:
+                assert pt == 0 and ns == 0                                             # no tile: no work
+                continue
+            pooled[bh, qb] += pt
+            if ns:
+                cover[bh][qb].append((off, ns))
+        if merge:                                   # two streams of ONE tile: stream 1 continues stream 0's slice
+            assert streams[0][0] == streams[1][0] and streams[1][2] == streams[0][2] + streams[0][3] and streams[1][3] > 0
+        if split:
+            slot, half = (split - 1) // 2, (split - 1) % 2
+            assert merge and streams[0][3] + streams[1][3] >= 2                        # both halves work on both streams
+            assert (slot, half) not in halves and 0 <= slot < min(G, 496)
+            halves[(slot, half)] = (bh, streams[0][0])
+    for (slot, half), tile in halves.items():
+        assert halves.get((slot, 1 - half)) == tile, "a half tile without its partner"
+    if not (dynamic and half_tiles):
+        assert not halves
+    assert (pooled == npt).all()
+    for bh in range(B * H):
+        b, h = divmod(bh, H)
+        for qb in range(nq):
+            segs = sorted(cover[bh][qb])
+            pos = 0
+            for off, ns in segs:
+                assert off == pos, (bh, qb, segs)
+                pos += ns
+            assert pos == int(cnt[b, h, qb]), (bh, qb, segs, int(cnt[b, h, qb]))

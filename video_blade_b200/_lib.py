@@ -55,6 +55,7 @@ SYMBOLS = [
     "blade_multilevel_pyramid", "blade_multilevel_mask", "blade_level_mask_to_index", "blade_multilevel_attn_fwd",
     "blade_multilevel_bwd_workspace_bytes", "blade_multilevel_attn_bwd",
     "blade_scaffold_ln_modulate", "blade_scaffold_rmsnorm", "blade_scaffold_gated_residual",
+    "blade_debug_attn_schedule",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
     lib.blade_asa_forward.argtypes = [T, T, T, vp, vp, CFG, vp, T, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.blade_profile_events.argtypes = [i32, vp, vp]
     lib.blade_probe_qk.argtypes = [vp, vp, vp, i32, vp]
+    lib.blade_debug_attn_schedule.argtypes = [i64, i64, i64, i32, i32, vp, i32, i32, vp, i64, vp]
     lib.blade_probe_pv.argtypes = [vp, vp, vp, i32, vp]
     lib.blade_mask64_to_index.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
     lib.blade_block_sparse_attn64_fwd.argtypes = lib.blade_block_sparse_attn_fwd.argtypes

@@ -197,6 +197,17 @@ __device__ __forceinline__ void transpose4x4(uint4 (&a)[4], int lane) {
   a[3] = lo ? t11 : x1;
 }
 
+// The item decode below is plain integer arithmetic shared by the three device roles AND by the host-side schedule
+// checker (blade_debug_attn_schedule, tests/test_host_logic.py): host + device, read-only loads through ld_ro.
+#define BLADE_HD __host__ __device__ __forceinline__
+template <typename T>
+BLADE_HD T ld_ro(const T* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 // One work item as the three roles see it: per stream t its query tile, how many pooled tiles it runs first,
 // and which slice [off, off + ns) of the row's block list it owns.
 struct Item {
@@ -218,7 +229,7 @@ struct Item {
 // ---- multi-level tiles: a level-L entry contributes the 128/L mean-pooled keys of its block; L consecutive entries of
 // one level are packed into ONE 128-key tensor-core tile (the softmax is order independent), so a row runs
 // n1 + ceil(n2/2) + ceil(n4/4) + ceil(n8/8) tiles.  Tile j -> level code lc = log2(L), first entry e0, entries ne.
-__device__ __forceinline__ int multi_tiles(const int4 c) {
+BLADE_HD int multi_tiles(const int4 c) {
   return c.x + ((c.y + 1) >> 1) + ((c.z + 3) >> 2) + ((c.w + 7) >> 3);
 }
 __device__ __forceinline__ void multi_tile(const int4 c, int j, int& lc, int& e0, int& ne) {
@@ -239,21 +250,21 @@ struct MultiMaps {
 // a query tile whose KV sequence is split across two CTAs, so that the last claims of a launch are quarter-length and
 // the tail of the persistent schedule is flat (3 heads on 148 CTAs = 2.59 rounds of pairs used to cost 3.1).
 // kind: 0 pair, 1 solo, 2 half; c = claim index of the pair slot; sub = which tile / half of it.
-__device__ __forceinline__ void classify(const AttnParams& p, int item, int& kind, int& c, int& sub) {
+BLADE_HD void classify(const AttnParams& p, int item, int& kind, int& c, int& sub) {
   const int s0 = p.num_pair_items, s1 = s0 + 2 * p.num_solo_pairs;
   if (item < s0) { kind = 0; c = item; sub = 0; }
   else if (item < s1) { kind = 1; c = s0 + ((item - s0) >> 1); sub = (item - s0) & 1; }
   else { kind = 2; c = s0 + p.num_solo_pairs + ((item - s1) >> 2); sub = (item - s1) & 3; }
 }
-__device__ __forceinline__ int pair_id_of(const AttnParams& p, int c) {
+BLADE_HD int pair_id_of(const AttnParams& p, int c) {
   const int bh_n = p.B * p.H, pph = p.pairs_per_head;
   if (pph == 1) return c;
   if (c < bh_n) return c * pph;
   const int j = c - bh_n;
   return (j / (pph - 1)) * pph + 1 + j % (pph - 1);
 }
-__device__ __forceinline__ int tile_of(const AttnParams& p, int pair, int t) { return p.nq - 1 - (2 * pair + t); }
-__device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& c0, int& c1) {
+BLADE_HD int tile_of(const AttnParams& p, int pair, int t) { return p.nq - 1 - (2 * pair + t); }
+BLADE_HD void item_counts(const AttnParams& p, int item, int& c0, int& c1) {
   c0 = c1 = 0;
   if (item >= p.num_items) return;
   int kind, c, sub;
@@ -263,19 +274,19 @@ __device__ __forceinline__ void item_counts(const AttnParams& p, int item, int& 
   if (kind == 0) {
     if (p.cnt4) {  // multi-level: tile counts from the per-level entry counts
       const int4* row4 = p.cnt4 + static_cast<int64_t>(bh) * p.nq;
-      c0 = multi_tiles(__ldg(row4 + tile_of(p, pair, 0)));
-      if (2 * pair + 1 < p.nq) c1 = multi_tiles(__ldg(row4 + tile_of(p, pair, 1)));
+      c0 = multi_tiles(ld_ro(row4 + tile_of(p, pair, 0)));
+      if (2 * pair + 1 < p.nq) c1 = multi_tiles(ld_ro(row4 + tile_of(p, pair, 1)));
       return;
     }
     const int32_t* row = p.cnt + static_cast<int64_t>(bh) * p.nq;
-    c0 = __ldg(row + tile_of(p, pair, 0));
-    if (2 * pair + 1 < p.nq) c1 = __ldg(row + tile_of(p, pair, 1));
+    c0 = ld_ro(row + tile_of(p, pair, 0));
+    if (2 * pair + 1 < p.nq) c1 = ld_ro(row + tile_of(p, pair, 1));
   } else {
     const int qb = tile_of(p, pair, kind == 1 ? sub : (sub >> 1));
-    if (qb >= 0) c0 = c1 = __ldg(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
+    if (qb >= 0) c0 = c1 = ld_ro(p.cnt + static_cast<int64_t>(bh) * p.nq + qb);
   }
 }
-__device__ __forceinline__ Item make_item(const AttnParams& p, int item, int c0, int c1) {
+BLADE_HD Item make_item(const AttnParams& p, int item, int c0, int c1) {
   Item it;
   const int npt = p.n_pool_tiles;
   int kind, cl, sub;
@@ -1147,6 +1158,32 @@ size_t attn_park_bytes(int64_t D) {
 }
 size_t attn_sched_bytes() { return kSchedBytes; }
 
+// Tail classes of a launch: how many of the np tile pairs are issued as solo tiles (two items per pair) and as half tiles
+// (four items per pair) behind the ordinary pair items.  Pure host arithmetic (also used by the schedule checker).
+static void plan_tail(int np, int G, bool no_split, bool can_x, bool multi, bool dynamic, int xmax, int env_xs, int env_solo,
+                      int& split, int& xsplit) {
+  split = xsplit = 0;
+  if (no_split || multi) return;  // multi-level rows are not split across the two streams
+  const int r = np % G;
+  if (can_x) {
+    if (np >= G) {
+      // measured (tools/sweep_xsplit.sh, profiles/r02z_sweep_xsplit.log): G/8 pairs of half tiles behind G pairs of
+      // solo tiles is best or within noise of best for 12 and 3 Wan heads, uniform and non-uniform rows, and CogVideoX
+      const int want_x = env_xs >= 0 ? env_xs : G / 8, want_s = env_solo >= 0 ? env_solo : G;
+      xsplit = want_x < xmax ? want_x : xmax;
+      xsplit = xsplit < np ? xsplit : np;
+      split = want_s < np - xsplit ? want_s : np - xsplit;
+    } else if (2 * np <= G && 4 * np > G) {
+      split = np;                                   // one round of solo tiles already fills the machine
+    } else {
+      xsplit = np < xmax ? np : xmax;               // few pairs: quarter items
+      split = np - xsplit < G / 2 ? np - xsplit : G / 2;
+    }
+  } else if (np < G) split = 2 * np <= G ? np : 0;
+  else if (dynamic) split = (G * BLADE_SOLO_NUM / BLADE_SOLO_DEN) < np ? G * BLADE_SOLO_NUM / BLADE_SOLO_DEN : np;
+  else split = (r > 0 && 2 * r <= G) ? r : 0;
+}
+
 static float round_host(float x, bool bf16) {
   return bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
 }
@@ -1245,27 +1282,8 @@ int launch_attn(const BladeTensor* q, const BladeTensor* k, const BladeTensor* v
     static const int env_xs = getenv("BLADE_XSPLIT_PAIRS") ? atoi(getenv("BLADE_XSPLIT_PAIRS")) : -1;   // tuning knobs
     static const int env_solo = getenv("BLADE_SOLO_PAIRS") ? atoi(getenv("BLADE_SOLO_PAIRS")) : -1;
     int split = 0, xsplit = 0;
-    if (!no_split && !multi) {  // multi-level rows are not split across the two streams
-      const int r = np % G;
-      const int xmax = attn_max_split_tiles() / 2;   // pairs whose two tiles may be half-split
-      if (can_x) {
-        if (np >= G) {
-          // measured (tools/sweep_xsplit.sh, profiles/r02z_sweep_xsplit.log): G/8 pairs of half tiles behind G pairs of
-          // solo tiles is best or within noise of best for 12 and 3 Wan heads, uniform and non-uniform rows, and CogVideoX
-          const int want_x = env_xs >= 0 ? env_xs : G / 8, want_s = env_solo >= 0 ? env_solo : G;
-          xsplit = want_x < xmax ? want_x : xmax;
-          xsplit = xsplit < np ? xsplit : np;
-          split = want_s < np - xsplit ? want_s : np - xsplit;
-        } else if (2 * np <= G && 4 * np > G) {
-          split = np;                                   // one round of solo tiles already fills the machine
-        } else {
-          xsplit = np < xmax ? np : xmax;               // few pairs: quarter items
-          split = np - xsplit < G / 2 ? np - xsplit : G / 2;
-        }
-      } else if (np < G) split = 2 * np <= G ? np : 0;
-      else if (p.sched) split = (G * BLADE_SOLO_NUM / BLADE_SOLO_DEN) < np ? G * BLADE_SOLO_NUM / BLADE_SOLO_DEN : np;
-      else split = (r > 0 && 2 * r <= G) ? r : 0;
-    }
+    plan_tail(np, G, no_split, can_x, multi != nullptr, p.sched != nullptr, attn_max_split_tiles() / 2, env_xs, env_solo, split,
+              xsplit);
     p.num_pair_items = np - split - xsplit;
     p.num_solo_pairs = split;
     p.num_split_pairs = xsplit;
@@ -1408,6 +1426,50 @@ extern "C" int blade_asa_attn_fwd(const BladeTensor* q, const BladeTensor* k, co
   BLADE_REQUIRE(sample_gap > 0 && k_pool && v_pool, BLADE_ERR_ARG, "pooled branch inputs missing");
   return launch_attn(q, k, v, idx, cnt, idx_stride, k_pool, v_pool, sample_gap, out, nullptr, dst_row, softmax_scale,
                      exact_merge, workspace, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+// Host-side replay of a launch's work-item decode: the SAME classify / pair_id_of / item_counts / make_item code the three
+// device roles run, on host counts -- so tests can check, without a GPU, that every query tile's pooled tiles and block
+// list are covered exactly once for any (B, H, nq, counts, SM count), half tiles included.
+extern "C" int blade_debug_attn_schedule(int64_t B, int64_t H, int64_t nq, int32_t n_pool_tiles, int32_t sm_count,
+                                         const int32_t* cnt_host, int32_t dynamic_queue, int32_t half_tiles,
+                                         int32_t* items_out, int64_t max_items, int32_t* n_items_out) {
+  BLADE_REQUIRE(B >= 1 && H >= 1 && nq >= 1 && sm_count >= 1 && n_pool_tiles >= 0 && cnt_host && items_out && n_items_out,
+                BLADE_ERR_ARG, "bad argument");
+  AttnParams p{};
+  p.B = static_cast<int>(B);
+  p.H = static_cast<int>(H);
+  p.nq = static_cast<int>(nq);
+  p.n_pool_tiles = n_pool_tiles;
+  p.pairs_per_head = static_cast<int>((nq + 1) / 2);
+  p.cnt = cnt_host;
+  const int np = static_cast<int>(B * H) * p.pairs_per_head, G = sm_count;
+  const int xmax = (G < kMaxSplitTiles ? G : kMaxSplitTiles) / 2;
+  int split = 0, xsplit = 0;
+  plan_tail(np, G, false, dynamic_queue != 0 && half_tiles != 0, false, dynamic_queue != 0, xmax, -1, -1, split, xsplit);
+  p.num_pair_items = np - split - xsplit;
+  p.num_solo_pairs = split;
+  p.num_split_pairs = xsplit;
+  p.num_items = p.num_pair_items + 2 * split + 4 * xsplit;
+  *n_items_out = p.num_items;
+  BLADE_REQUIRE(p.num_items <= max_items, BLADE_ERR_WORKSPACE, "%d items, room for %lld", p.num_items, (long long)max_items);
+  for (int item = 0; item < p.num_items; ++item) {
+    int c0, c1;
+    item_counts(p, item, c0, c1);
+    const Item it = make_item(p, item, c0, c1);
+    int32_t* o = items_out + static_cast<int64_t>(item) * 12;
+    o[0] = item;
+    o[1] = it.bh;
+    for (int t = 0; t < 2; ++t) {
+      o[2 + 4 * t] = it.qb[t];
+      o[3 + 4 * t] = it.pt[t];
+      o[4 + 4 * t] = it.off[t];
+      o[5 + 4 * t] = it.ns[t];
+    }
+    o[10] = it.merge ? 1 : 0;
+    o[11] = it.split ? 1 + 2 * it.slot + it.half : 0;
+  }
+  return BLADE_OK;
 }
 
 #ifdef BLADE_TRACE
