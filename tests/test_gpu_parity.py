@@ -336,6 +336,42 @@ def test_sampled_max_estimator_vs_oracle(flavor, grid, T, H, D):
     _close(out, ref.out)
 
 
+def test_estimator_kernel_variants_agree_bit_for_bit():
+    """The three builds of the sampled-max score kernel -- v2 (default: Q and R in TMEM, TS-mode MMA, full-smem ring), v1
+    (`BLADE_EST_V1=1`: Q and R in shared memory) and v1 inside a 2-CTA cluster with TMA multicast of the key tiles
+    (`BLADE_EST_CLUSTER=2`) -- run the same MMAs and the same roundings: identical scores, including a ragged block count
+    (nb = 139: an odd number of query tiles, padded for the cluster) and d = 64."""
+    import os, subprocess, sys
+    code = (
+        "import torch, sys; sys.path.insert(0, '.');"
+        "from video_blade_b200.asa import AsaEngine, AsaKnobs;"
+        "from video_blade_b200.synth import synth_qkv;"
+        "outs = [];\n"
+        "for flavor, H, D, S in (('wan', 2, 128, 26*15*16), ('cog', 3, 64, 17776)):\n"
+        "    kn = AsaKnobs.wan(width=26, height=15, depth=16) if flavor == 'wan' else AsaKnobs.cog()\n"
+        "    kn.estimator = 'sampled_max'\n"
+        "    eng = AsaEngine(kn)\n"
+        "    q, k, v = synth_qkv(1, H, S, D, seed=31, structured=2.0)\n"
+        "    g = torch.Generator(device='cuda').manual_seed(5)\n"
+        "    qo, ko = eng.draw_offsets(1, H, 'cuda', g), eng.draw_offsets(1, H, 'cuda', g)\n"
+        "    outs.append(eng.scores_sampled(q.cuda(), k.cuda(), qo, ko).cpu())\n"
+        "torch.save(outs, sys.argv[1])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for i, extra in enumerate(({}, {"BLADE_EST_V1": "1"}, {"BLADE_EST_V1": "1", "BLADE_EST_CLUSTER": "2"})):
+        path = os.path.join(root, "tests", f"_est_{i}.pt")
+        env = dict(os.environ, **extra)
+        for key in ("BLADE_EST_V1", "BLADE_EST_CLUSTER"):
+            if key not in extra:
+                env.pop(key, None)
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=env, timeout=300)
+        res.append(torch.load(path))
+        os.remove(path)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert not torch.isnan(a).any() and torch.equal(a, b)
+
+
 def test_sampled_offsets_follow_reference_distribution():
     eng = _engine(estimator="sampled_max")
     off = eng.draw_offsets(2, 3, torch.device("cuda"))
@@ -586,6 +622,20 @@ def test_half_tile_items_vs_torch_fp32_and_run_to_run_identical():
     _close(got, O.merge_lse(wout, wlse.unsqueeze(-1).to(q2.dtype), o2, l2.unsqueeze(-1).to(q2.dtype), 30))
     for _ in range(5):
         assert torch.equal(eng.asa_attn(q2.cuda(), k2.cuda(), v2.cuda(), i2.cuda(), c2.cuda(), kp2.cuda(), vp2.cuda()), got)
+    # (c) d = 64, fp16, 75 pairs per head x 2 heads: pairs + solo + half tiles, against fp32 torch attention
+    S3, H3, D3, nb3 = 150 * 128, 2, 64, 150
+    q3, k3, v3 = (torch.randn(1, S3, H3, D3, device="cuda", generator=g).to(torch.float16).transpose(1, 2) for _ in range(3))
+    sc3 = torch.rand(1, H3, nb3, nb3, device="cuda", generator=g)
+    c3 = torch.randint(4, 25, (1, H3, nb3, 1), device="cuda", generator=g)
+    m3 = sc3 >= torch.sort(sc3, dim=-1, descending=True).values.gather(-1, c3 - 1)
+    i3, n3 = eng.mask_to_index(m3)
+    o3, l3 = eng.block_sparse_attn(q3, k3, v3, i3, n3)
+    for h in range(H3):
+        tok = m3[0, h].repeat_interleave(128, 0).repeat_interleave(128, 1)
+        s_ = (q3[0, h].float() @ k3[0, h].float().T) / D3 ** 0.5
+        s_ = s_.masked_fill(~tok, float("-inf"))
+        _close(o3[0, h], (torch.softmax(s_, -1) @ v3[0, h].float()).to(torch.float16))
+        _close(l3[0, h], torch.logsumexp(s_, -1), 1e-5, 1e-4)
 
 
 # ------------------------------------------------------------------ the benchmarked sizes (BASELINE configs 2 and 4)
