@@ -174,6 +174,47 @@ def test_block_sparse_attn_dense_mask_batch2_strided():
     _close(out, ref.to(q.dtype))
 
 
+@pytest.mark.parametrize("D", [128, 64])
+def test_block_sparse_attn_vs_flash_attention_library(D):
+    """Pin for the one "parity unpinned" function: the reference's `block_sparse_attn_func` is the mit-han-lab fork of the
+    FlashAttention-2 CUDA kernels (absent here), FlashAttention-2 itself is installed in this image.  (a) all-ones mask
+    (the reference's `standard_attn`, W:21-24): output AND natural-log LSE against `flash_attn_func`; (b) random block
+    masks: for several query tiles the selected key blocks are gathered into a contiguous K', V' and the tile is run
+    through dense `flash_attn_func` -- block-sparse attention by construction.  Library use is confined to this test."""
+    fa = pytest.importorskip("flash_attn")
+    eng = _engine(use_rearrange=False)
+    B, H, S, nb = 1, 2, 2048, 16
+    g = torch.Generator(device="cuda").manual_seed(41 + D)
+    q, k, v = (torch.randn(B, S, H, D, device="cuda", generator=g).to(torch.bfloat16) for _ in range(3))   # [B,S,H,D]
+    qh, kh, vh = (x.transpose(1, 2) for x in (q, k, v))                                                     # [B,H,S,D] views
+    try:
+        ref, ref_lse, _ = fa.flash_attn_func(q, k, v, return_attn_probs=True)
+    except RuntimeError as e:                                    # the wheel has no kernel for this GPU
+        pytest.skip(f"flash_attn cannot run here: {e}")
+    idx, cnt = eng.mask_to_index(torch.ones(B, H, nb, nb, dtype=torch.bool, device="cuda"))
+    out, lse = eng.block_sparse_attn(qh, kh, vh, idx, cnt)
+    d = out.float() - ref.transpose(1, 2).float()
+    assert float(d.norm() / ref.float().norm()) <= 5e-3 and float(d.abs().max()) <= MAX_ABS
+    assert float((lse - ref_lse).abs().max()) <= 2e-3
+    # (b) random block masks, rows keeping 1..12 of 16 blocks
+    score = torch.rand(B, H, nb, nb, device="cuda", generator=g)
+    counts = torch.randint(1, 13, (B, H, nb, 1), device="cuda", generator=g)
+    mask = score >= torch.sort(score, dim=-1, descending=True).values.gather(-1, counts - 1)
+    idx, cnt = eng.mask_to_index(mask)
+    out, lse = eng.block_sparse_attn(qh, kh, vh, idx, cnt)
+    for h in range(H):
+        for qb in (0, 5, 15):
+            sel = torch.nonzero(mask[0, h, qb]).flatten().tolist()
+            rows = torch.cat([torch.arange(j * 128, (j + 1) * 128) for j in sel]).cuda()
+            qt = q[:, qb * 128:(qb + 1) * 128, h:h + 1].contiguous()
+            kt, vt = k[:, rows, h:h + 1].contiguous(), v[:, rows, h:h + 1].contiguous()
+            r_o, r_l, _ = fa.flash_attn_func(qt, kt, vt, return_attn_probs=True)
+            got = out[0, h, qb * 128:(qb + 1) * 128].float()
+            dd = got - r_o[0, :, 0].float()
+            assert float(dd.norm() / r_o.float().norm()) <= 5e-3 and float(dd.abs().max()) <= MAX_ABS, (h, qb)
+            assert float((lse[0, h, qb * 128:(qb + 1) * 128] - r_l[0, 0]).abs().max()) <= 2e-3, (h, qb)
+
+
 @pytest.mark.parametrize("flavor,D,H,S,gap", [("wan", 128, 2, 1560, 30), ("cog", 64, 3, 940, 15), ("wan", 128, 1, 4000, 30)])
 def test_asa_attn_pooled_merge_vs_oracle(flavor, D, H, S, gap):
     eng = _engine(flavor=flavor, use_rearrange=False, sample_gap=gap)
